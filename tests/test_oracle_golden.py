@@ -1,0 +1,140 @@
+"""Pin the C oracle (oracle/tetris_oracle.c) to fixtures recorded from the live Python
+reference (tests/golden/make_golden.py).  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from golden_util import TRACES, feat2, load, rep_to_rows, rows_to_rep
+from oracle import oracle as orc
+
+
+def test_afterstate_counts():
+    # A per piece at C=10 and C=6
+    assert [orc.num_afterstates(p, 10) for p in range(9)] == [17, 34, 34, 9, 17, 17, 34, 36, 18]
+    assert [orc.num_afterstates(p, 6) for p in range(9)] == [9, 18, 18, 5, 9, 9, 18, 20, 10]
+
+
+def test_empty_board_features():
+    # empty 10x20 board
+    assert orc.reset_state_features(10, 20).tolist() == [0, 10, 0, 1, 0, 40, 0, 0]
+
+
+def test_afterstates_fixture():
+    g = load("afterstates")
+    n_checked = 0
+    for i in range(len(g["piece"])):
+        C, R = (int(x) for x in g["shape"][i])
+        N = R + 4
+        rep = rows_to_rep(g["rows"][i][:N], C)
+        out = orc.afterstates(C, R, int(g["piece"][i]), rep, g["heights"][i][:C].astype(np.int32))
+        s, n = int(g["start"][i]), int(g["count"][i])
+        assert out["n"] == n
+        sl = slice(s, s + n)
+        assert np.array_equal(feat2(out["features"]), g["a_feat2"][sl])
+        assert np.array_equal(out["terminal"], g["a_terminal"][sl])
+        assert np.array_equal(out["n_cleared"], g["a_n_cleared"][sl])
+        assert np.array_equal(rep_to_rows(out["rep"]), g["a_rows"][sl][:, :N])
+        assert np.array_equal(out["heights"], g["a_heights"][sl][:, :C])
+        assert np.array_equal(out["anchor_col"], g["a_anchor"][sl][:, 0])
+        assert np.array_equal(out["anchor_row"], g["a_anchor"][sl][:, 1])
+        assert np.array_equal(out["is_full"], g["a_is_full"][sl])
+        n_checked += n
+    assert n_checked == len(g["a_terminal"]) > 30000
+
+
+def replay_trace(g, make_batch, rng_mode):
+    """Drive an engine with the fixture's piece/action tapes and compare after every step.
+
+    make_batch(C, R, n_env, piece_set, seed) must return an object with the oracle.Batch API.
+    rng_mode: pieces come from the engine's own bag RNG (must reproduce the tape) instead of the tape.
+    """
+    C, R, ps, seed = int(g["C"]), int(g["R"]), int(g["piece_set"]), int(g["seed"])
+    T, n = g["action"].shape
+    b = make_batch(C, R, n, ps, seed)
+    b.reset(None if rng_mode else g["piece"][0].astype(np.uint8))
+    for t in range(T):
+        assert np.array_equal(b.piece, g["piece"][t]), t
+        feats, valid, count, n_all = b.afterstates()
+        assert np.array_equal(count, g["n_valid"][t]), t
+        assert np.array_equal(n_all, g["n_all"][t]), t
+        a_max = g["feat2"].shape[2]
+        vbits = ((valid[:, None] >> np.arange(a_max, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+        assert np.array_equal(vbits, g["valid"][t]), t
+        for e in range(n):
+            na = int(n_all[e])
+            assert np.array_equal(feat2(feats[e, :na]), g["feat2"][t, e, :na]), (t, e)
+        if str(g["policy"]) == "greedy":
+            # the recorded action must be the first arg-max of the float32 fitness over valid afterstates
+            for e in range(n):
+                fv = [orc.fitness(feats[e, s], orc.BCTS_WEIGHTS) for s in range(int(n_all[e])) if vbits[e, s]]
+                assert int(np.argmax(np.array(fv, np.float32))) == int(g["action"][t, e]), (t, e)
+        tape = None if rng_mode else g["next_piece"][t].astype(np.uint8)
+        obs, reward, done, lines = b.step(g["action"][t].astype(np.int32), tape=tape)
+        assert np.array_equal(feat2(obs), g["obs2"][t]), t
+        assert np.array_equal(reward, g["reward"][t]), t
+        assert np.array_equal(done, g["done"][t]), t
+        assert np.array_equal(lines, g["lines"][t]), t
+        assert np.array_equal(b.rows(), g["rows"][t]), t
+        assert np.array_equal(b.heights, g["heights"][t]), t
+        assert np.array_equal(b.piece, g["next_piece"][t]), t
+        if done.any():
+            rp = g["reset_piece"][t]
+            b.reset_masked(done, None if rng_mode else np.where(rp >= 0, rp, 0).astype(np.uint8))
+            assert np.array_equal(b.piece[done], rp[done]), t
+
+
+def _oracle_batch(C, R, n, ps, seed):
+    return orc.Batch(C, R, n, piece_set=ps, seed=seed)
+
+
+@pytest.mark.parametrize("name", TRACES)
+def test_trace_tape(name):
+    replay_trace(load("trace_" + name), _oracle_batch, rng_mode=False)
+
+
+@pytest.mark.parametrize("name", TRACES)
+def test_trace_rng(name):
+    """The oracle's own per-env bag RNG reproduces the recorded piece tape."""
+    replay_trace(load("trace_" + name), _oracle_batch, rng_mode=True)
+
+
+def test_known_answer():
+    """SURVEY.md Appendix C.3 (reference sampler, np.random.seed(0)) replayed from the piece tape."""
+    g = load("known_answer")
+    d = np.array([-1, -1, -1, -1, -1, -1, 1, -1], np.float64)
+    b = orc.Batch(10, 10, 1, piece_set=0)
+    b.reset(np.array([g["first_piece"]], np.uint8))
+    hsh = hashlib.sha256()
+    total = 0
+    for t in range(len(g["action"])):
+        feats, valid, count, n_all = b.afterstates()
+        vf = np.array([feats[0, s] for s in range(int(n_all[0])) if (int(valid[0]) >> s) & 1], np.float32) * d
+        assert len(vf) == g["n_valid"][t]
+        i = int(np.argmax(vf.sum(axis=1)))
+        assert i == g["action"][t]
+        obs, reward, done, lines = b.step(np.array([i], np.int32), tape=np.array([g["next_piece"][t]], np.uint8))
+        o = obs[0] * d
+        assert np.array_equal(o, g["obs"][t]) and np.array_equal(np.signbit(o), np.signbit(g["obs"][t]))
+        assert reward[0] == g["reward"][t] and lines[0] == g["lines"][t] and bool(done[0]) == bool(g["done"][t])
+        hsh.update(b.rep[0].astype(np.uint8).tobytes())
+        hsh.update(np.asarray(o, np.float64).tobytes())
+        total += int(reward[0])
+        if done[0]:
+            b.reset_masked(done, np.array([g["reset_piece"][t]], np.uint8))
+    assert total == -71
+    assert hsh.hexdigest() == str(g["sha256"])
+    assert np.array_equal(b.rows()[0], g["final_rows"])
+    assert b.rows()[0][:2].tolist() == [807, 519]
+
+
+def test_fitness_fixture():
+    g = load("fitness")
+    C, R = int(g["C"]), int(g["R"])
+    for i in range(len(g["piece"])):
+        out = orc.afterstates(C, R, int(g["piece"][i]), rows_to_rep(g["rows"][i], C))
+        s, n = int(g["start"][i]), int(g["count"][i])
+        fv = np.array([orc.fitness(f, orc.BCTS_WEIGHTS) for f in out["features"]], np.float32)
+        assert np.array_equal(fv, g["fitness"][s:s + n])          # bit-exact float32
+        pol = (fv == fv.max()).astype(float)
+        assert np.array_equal(pol / pol.sum(), g["best_policy"][s:s + n])
