@@ -1,0 +1,95 @@
+// hostcheck.cpp -- TEST-ONLY.  Compiles the product's host/device core header (tb_core.cuh) with g++
+// so the bit-parallel math the CUDA kernels execute can be checked against the oracle on a machine
+// without a GPU.  Nothing in tetris_b200 loads this library.
+#include <cstdint>
+#include <cstring>
+#include "../../tetris_b200/csrc/tb_core.cuh"
+
+using namespace tb;
+
+template <int C, int R>
+static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats, uint8_t *terminal,
+                         int32_t *ncleared, uint16_t *rows_out, int32_t *anchor, uint8_t *used_fast)
+{
+    using S = Shape<C, R>;
+    uint32_t w[S::NW];
+    std::memset(w, 0, sizeof w);
+    for (int r = 0; r < S::N; ++r) w[r >> 1] |= (uint32_t)rows[r] << (16 * (r & 1));
+    uint32_t col[C];
+    rows_to_cols<C, R>(w, col);
+    uint32_t rec[Rec<C, R>::WORDS + 8];
+    std::memset(rec, 0, sizeof rec);
+    build_env<C, R>(col, rec);
+    const uint32_t pw = kPieceHost[piece];
+    const int n = piece_num_slots(pw, C);
+    for (int s = 0; s < n; ++s) {
+        int ori, c;
+        slot_to_placement(pw, C, s, ori, c);
+        const uint32_t d = kOriHost[ori];
+        Eval e;
+        uint32_t nc[C];
+        bool fast = (mode == 0) && eval_fast<C, R>(rec, d, c, e);
+        if (!fast) eval_slow<C, R>(col, d, c, e, nc);
+        else {
+            // afterstate board of a fast-path placement: place without clearing
+            Eval e2; eval_slow<C, R>(col, d, c, e2, nc);
+        }
+        std::memcpy(feats + 8 * s, e.f, sizeof e.f);
+        terminal[s] = (uint8_t)e.terminal;
+        ncleared[s] = popc32(e.full);
+        anchor[s] = e.a;
+        used_fast[s] = fast;
+        uint32_t wo[S::NW];
+        cols_to_rows<C, R>(nc, wo);
+        for (int r = 0; r < S::N; ++r) rows_out[s * S::N + r] = (uint16_t)(wo[r >> 1] >> (16 * (r & 1)));
+        // placement_valid must agree with the terminal flag
+        int h[C];
+        for (int k = 0; k < C; ++k) h[k] = height_of(col[k]);
+        if (placement_valid<C, R>(col, h, d, c) != (e.terminal == 0)) return -1;
+    }
+    return n;
+}
+
+#define SHAPES(X) X(10, 20) X(10, 10) X(6, 12) X(8, 16) X(4, 4)
+
+extern "C" int hc_afterstates(int C, int R, int piece, const uint16_t *rows, int mode, float *feats,
+                              uint8_t *terminal, int32_t *ncleared, uint16_t *rows_out, int32_t *anchor,
+                              uint8_t *used_fast)
+{
+#define X(c, r) if (C == c && R == r) return afterstates_t<c, r>(piece, rows, mode, feats, terminal, ncleared, rows_out, anchor, used_fast);
+    SHAPES(X)
+#undef X
+    return -2;
+}
+
+template <int C, int R>
+static int transpose_t(const uint16_t *rows, uint16_t *rows_back, uint32_t *cols_out)
+{
+    using S = Shape<C, R>;
+    uint32_t w[S::NW], w2[S::NW], col[C];
+    std::memset(w, 0, sizeof w);
+    for (int r = 0; r < S::N; ++r) w[r >> 1] |= (uint32_t)rows[r] << (16 * (r & 1));
+    rows_to_cols<C, R>(w, col);
+    for (int c = 0; c < C; ++c) cols_out[c] = col[c];
+    cols_to_rows<C, R>(col, w2);
+    for (int r = 0; r < S::N; ++r) rows_back[r] = (uint16_t)(w2[r >> 1] >> (16 * (r & 1)));
+    return 0;
+}
+extern "C" int hc_transpose(int C, int R, const uint16_t *rows, uint16_t *rows_back, uint32_t *cols_out)
+{
+#define X(c, r) if (C == c && R == r) return transpose_t<c, r>(rows, rows_back, cols_out);
+    SHAPES(X)
+#undef X
+    return -2;
+}
+
+extern "C" uint32_t hc_rng(uint64_t seed, uint64_t env, uint32_t ctr, uint32_t stream)
+{
+    return rng32(env_key(seed, env), ctr, stream);
+}
+extern "C" int hc_bag_draw(int n_set, uint64_t seed, uint64_t env, uint32_t *bag, uint32_t *draws)
+{
+    return bag_draw(n_set, env_key(seed, env), *bag, *draws);
+}
+extern "C" float hc_fitness(const float *f, const float *w) { return fitness(f, w); }
+extern "C" int hc_num_slots(int piece, int C) { return piece_num_slots(kPieceHost[piece], C); }

@@ -1,0 +1,638 @@
+// tb_core.cuh -- bit-parallel Tetris afterstate/step math shared by every sm_100a kernel.
+//
+// Everything here is __host__ __device__ so the exact code the kernels run can also be
+// compiled with g++ and checked against the CPU oracle without a GPU (tests/hostcheck).
+// It is NOT a CPU product path: tetris_b200 only ever calls the CUDA kernels.
+//
+// Board model: C columns x R legal rows + 4 buffer rows (game.py:56),
+// row 0 = bottom.  Compute form is one 32-bit mask per column (bit r = cell (r, c)); the
+// HBM form is one uint16 mask per row, eight rows per 128-bit word (see tb_kernels.cu).
+//
+// Reference semantics restated in bit-parallel form (file:line into the reference):
+//   piece x orientation tables ............ tetromino.py:33-576   (kOri / kPiece below)
+//   hard drop by column heights ........... tetromino.py e.g. :349,:365 (anchor_row = max(h - bottom))
+//   clear_lines_jitted .................... state.py:121-143      (full = AND of column masks)
+//   check_terminal ........................ state.py:111-117      (any cell in row R after clearing)
+//   get_feature_values_jitted ............. state.py:175-280      (eval_full / eval_fast)
+//   calc_bcts_features .................... state.py:97-107       (landing height, eroded)
+//   TetrominoSampler (bag) ................ tetromino.py:12-22    (bag_draw; per-env counter RNG)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TB_HD __host__ __device__ __forceinline__
+#else
+#define TB_HD inline
+#endif
+
+namespace tb {
+
+// ---------------------------------------------------------------------------------------------
+// bit helpers
+// ---------------------------------------------------------------------------------------------
+TB_HD int popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+TB_HD int clz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+TB_HD int ctz32(uint32_t x)  // x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+TB_HD uint32_t mask_lo(int k) { return (1u << k) - 1u; }          // k in [0, 31]
+TB_HD int height_of(uint32_t col) { return 32 - clz32(col); }      // 1 + highest filled row, 0 if empty
+TB_HD int imax(int a, int b) { return a > b ? a : b; }
+TB_HD int imin(int a, int b) { return a < b ? a : b; }
+
+// cumulative-wells run sum (state.py:227-229,262-272): every maximal vertical run of well
+// cells of length L adds 1+2+..+L.  sum_k popc(W_k), W_0 = W, W_{k+1} = W_k & (W_k >> 1).
+TB_HD int run_sum(uint32_t w)
+{
+    int s = 0;
+    while (w) { s += popc32(w); w &= w >> 1; }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// piece x orientation tables (tetromino.py).  Global piece ids: 0..6 = the 7-piece order of
+// game.py:41-47 (Straight, RCorner, LCorner, Square, SnakeR, SnakeL, T); 7,8 = the default set
+// of game.py:38-39 (ThreeL, ThreeLine).
+// ---------------------------------------------------------------------------------------------
+constexpr int kNumPieces = 9;
+constexpr int kNumOris = 25;
+
+// Orientation descriptor, one 32-bit word:
+//   [0:3)  w       width in columns
+//   [3:23) 4 x 5b  per piece column dx: bottom offset (2b) | cell count (3b) << 2   (count 0 = absent)
+//   [23:26) chg    len(changed_lines)
+//   [26:28) bonus2 2 * landing_height_bonus
+//   [28:31) ph     piece height in rows
+struct OriDef { int w; int n; int cell[4][2]; int chg; int bonus2; };
+
+constexpr uint32_t pack_ori(OriDef d)
+{
+    uint32_t v = (uint32_t)d.w;
+    int ph = 0;
+    for (int dx = 0; dx < 4; ++dx) {
+        int bot = 9, top = -1;
+        for (int i = 0; i < d.n; ++i)
+            if (d.cell[i][0] == dx) {
+                if (d.cell[i][1] < bot) bot = d.cell[i][1];
+                if (d.cell[i][1] > top) top = d.cell[i][1];
+            }
+        if (top >= 0) {
+            v |= (uint32_t)(bot | ((top - bot + 1) << 2)) << (3 + 5 * dx);
+            if (top + 1 > ph) ph = top + 1;
+        }
+    }
+    return v | (uint32_t)d.chg << 23 | (uint32_t)d.bonus2 << 26 | (uint32_t)ph << 28;
+}
+
+// Enumeration order = reference action order: per piece 1-2 column loops; inside a loop the
+// orientations are emitted interleaved per column (tetromino.py e.g. :347-378).
+#define TB_ORI_TABLE(X)                                                      \
+    /* Straight :44-57, :60-74 */                                            \
+    X({1, 4, {{0,0},{0,1},{0,2},{0,3}}, 4, 3})                               \
+    X({4, 4, {{0,0},{1,0},{2,0},{3,0}}, 1, 0})                               \
+    /* RCorner :431-445, :447-460, :465-478, :480-494 */                     \
+    X({3, 4, {{0,0},{1,0},{2,0},{2,1}}, 1, 1})                               \
+    X({3, 4, {{0,0},{0,1},{1,1},{2,1}}, 2, 1})                               \
+    X({2, 4, {{0,2},{1,0},{1,1},{1,2}}, 3, 2})                               \
+    X({2, 4, {{0,0},{0,1},{0,2},{1,0}}, 1, 2})                               \
+    /* LCorner :511-525, :527-540, :545-559, :561-575 */                     \
+    X({3, 4, {{0,0},{1,0},{2,0},{0,1}}, 1, 1})                               \
+    X({3, 4, {{2,0},{0,1},{1,1},{2,1}}, 2, 1})                               \
+    X({2, 4, {{0,0},{0,1},{0,2},{1,2}}, 3, 2})                               \
+    X({2, 4, {{0,0},{1,0},{1,1},{1,2}}, 1, 2})                               \
+    /* Square :90-103 */                                                     \
+    X({2, 4, {{0,0},{1,0},{0,1},{1,1}}, 2, 1})                               \
+    /* SnakeR :120-135, :138-153 */                                          \
+    X({3, 4, {{0,0},{1,0},{1,1},{2,1}}, 1, 1})                               \
+    X({2, 4, {{0,1},{0,2},{1,0},{1,1}}, 2, 2})                               \
+    /* SnakeL :297-312, :315-330 */                                          \
+    X({3, 4, {{1,0},{2,0},{0,1},{1,1}}, 1, 1})                               \
+    X({2, 4, {{0,0},{0,1},{1,1},{1,2}}, 2, 2})                               \
+    /* T :348-362, :364-378, :383-397, :399-413 */                           \
+    X({3, 4, {{0,0},{1,0},{2,0},{1,1}}, 1, 1})                               \
+    X({3, 4, {{1,0},{0,1},{1,1},{2,1}}, 2, 1})                               \
+    X({2, 4, {{0,1},{1,0},{1,1},{1,2}}, 2, 2})                               \
+    X({2, 4, {{0,0},{0,1},{0,2},{1,1}}, 2, 2})                               \
+    /* ThreeL :216-230, :232-247, :252-266, :267-281 */                      \
+    X({2, 3, {{0,0},{1,0},{1,1},{0,0}}, 1, 1})                               \
+    X({2, 3, {{0,0},{0,1},{1,1},{0,0}}, 2, 1})                               \
+    X({2, 3, {{0,1},{1,0},{1,1},{0,0}}, 2, 1})                               \
+    X({2, 3, {{0,0},{0,1},{1,0},{0,0}}, 1, 1})                               \
+    /* ThreeLine :168-181, :184-198 */                                       \
+    X({1, 3, {{0,0},{0,1},{0,2},{0,0}}, 3, 2})                               \
+    X({3, 3, {{0,0},{1,0},{2,0},{0,0}}, 1, 0})
+
+// Piece word: [0:2) n0 orientations in loop 0, [2:5) w0, [5:7) n1, [7:10) w1, [10:16) first ori index.
+constexpr uint32_t pack_piece(int n0, int w0, int n1, int w1, int base)
+{
+    return (uint32_t)n0 | (uint32_t)w0 << 2 | (uint32_t)n1 << 5 | (uint32_t)w1 << 7 | (uint32_t)base << 10;
+}
+#define TB_PIECE_TABLE(X)                                                    \
+    X(pack_piece(1, 1, 1, 4, 0))   /* 0 Straight  */                         \
+    X(pack_piece(2, 3, 2, 2, 2))   /* 1 RCorner   */                         \
+    X(pack_piece(2, 3, 2, 2, 6))   /* 2 LCorner   */                         \
+    X(pack_piece(1, 2, 0, 1, 10))  /* 3 Square    */                         \
+    X(pack_piece(1, 3, 1, 2, 11))  /* 4 SnakeR    */                         \
+    X(pack_piece(1, 3, 1, 2, 13))  /* 5 SnakeL    */                         \
+    X(pack_piece(2, 3, 2, 2, 15))  /* 6 T         */                         \
+    X(pack_piece(2, 2, 2, 2, 19))  /* 7 ThreeL    */                         \
+    X(pack_piece(1, 1, 1, 3, 23))  /* 8 ThreeLine */
+
+#define TB_X_ORI(...) pack_ori(OriDef __VA_ARGS__),
+#define TB_X_PIECE(v) v,
+static constexpr uint32_t kOriHost[kNumOris] = { TB_ORI_TABLE(TB_X_ORI) };
+static constexpr uint32_t kPieceHost[kNumPieces] = { TB_PIECE_TABLE(TB_X_PIECE) };
+
+// piece sets (game.py:38-39 default, :41-47 seven pieces): local index -> global id
+constexpr int kSetSize[2] = { 2, 7 };
+TB_HD int set_piece(int piece_set, int idx) { return piece_set == 0 ? 7 + idx : idx; }
+TB_HD int set_size(int piece_set) { return piece_set == 0 ? 2 : 7; }
+
+TB_HD int desc_w(uint32_t d) { return (int)(d & 7u); }
+TB_HD int desc_bot(uint32_t d, int dx) { return (int)((d >> (3 + 5 * dx)) & 3u); }
+TB_HD int desc_len(uint32_t d, int dx) { return (int)((d >> (5 + 5 * dx)) & 7u); }
+TB_HD int desc_chg(uint32_t d) { return (int)((d >> 23) & 7u); }
+TB_HD int desc_bonus2(uint32_t d) { return (int)((d >> 26) & 3u); }
+TB_HD int desc_ph(uint32_t d) { return (int)((d >> 28) & 7u); }
+
+// number of afterstates of a piece on C columns
+TB_HD int piece_num_slots(uint32_t pw, int C)
+{
+    const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7;
+    return n0 * (C - w0 + 1) + n1 * (C - w1 + 1);
+}
+// enumeration slot -> (orientation table index, anchor column)
+TB_HD void slot_to_placement(uint32_t pw, int C, int slot, int &ori, int &c)
+{
+    const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, base = (pw >> 10) & 63;
+    const int s0 = n0 * (C - w0 + 1);
+    if (slot < s0) { c = slot >> (n0 - 1); ori = base + (slot & (n0 - 1)); }
+    else { const int s = slot - s0; c = s >> (n1 - 1); ori = base + n0 + (s & (n1 - 1)); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-env counter-based RNG + shuffled bag (replaces NumPy's global MT19937 behind
+// TetrominoSampler, tetromino.py:12-22; restated on the CPU in oracle/tetris_oracle.c).
+// ---------------------------------------------------------------------------------------------
+TB_HD uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+TB_HD uint64_t env_key(uint64_t seed, uint64_t env) { return mix64(seed + 0x9E3779B97F4A7C15ULL * (env + 1)); }
+TB_HD uint32_t rng32(uint64_t key, uint32_t ctr, uint32_t stream)
+{
+    return (uint32_t)(mix64(key ^ (((uint64_t)stream << 32) | (uint64_t)ctr)) >> 32);
+}
+TB_HD uint32_t bounded(uint32_t r, uint32_t k) { return (uint32_t)(((uint64_t)r * (uint64_t)k) >> 32); }
+
+// Draw the next local piece index: refill the bag when empty, pick the j-th remaining piece.
+TB_HD int bag_draw(int n_set, uint64_t key, uint32_t &bag, uint32_t &draws)
+{
+    if (bag == 0) bag = (1u << n_set) - 1u;
+    const uint32_t j = bounded(rng32(key, draws, 0u), (uint32_t)popc32(bag));
+    draws += 1;
+    uint32_t b = bag;
+    for (uint32_t i = 0; i < j; ++i) b &= b - 1;
+    const int idx = ctz32(b);
+    bag &= ~(1u << idx);
+    return idx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-mask <-> column-mask transposition.
+// HBM holds rows packed two per 32-bit word (row 2k in the low half), 8 rows per 128-bit plane.
+// ---------------------------------------------------------------------------------------------
+TB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+#endif
+}
+// 8x8 bit-matrix transpose of the 64-bit matrix (lo = rows 0-3, hi = rows 4-7, one byte per row).
+TB_HD void transpose8(uint32_t &lo, uint32_t &hi)
+{
+    uint32_t t;
+    t = (lo ^ (lo >> 7)) & 0x00AA00AAu; lo ^= t ^ (t << 7);
+    t = (hi ^ (hi >> 7)) & 0x00AA00AAu; hi ^= t ^ (t << 7);
+    t = (lo ^ (lo >> 14)) & 0x0000CCCCu; lo ^= t ^ (t << 14);
+    t = (hi ^ (hi >> 14)) & 0x0000CCCCu; hi ^= t ^ (t << 14);
+    t = (hi & 0xF0F0F0F0u) | ((lo >> 4) & 0x0F0F0F0Fu);
+    lo = (lo & 0x0F0F0F0Fu) | ((hi << 4) & 0xF0F0F0F0u);
+    hi = t;
+}
+
+template <int C, int R>
+struct Shape {
+    static constexpr int N = R + 4;                      // stored rows (game.py:56)
+    static constexpr int NB = (N + 7) / 8;               // 8-row blocks = 128-bit planes per env
+    static constexpr int NW = NB * 4;                    // packed 32-bit words per env
+    static constexpr uint32_t ALL = (N >= 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
+    static constexpr uint32_t FULLROW = (1u << C) - 1u;
+    static_assert(C >= 4 && C <= 10, "supported widths: 4..10 columns");
+    static_assert(N <= 24 && R >= 4, "supported heights: 4..20 rows (+4 buffer rows)");
+};
+
+// rows (packed words w[NW]) -> column masks col[C]
+template <int C, int R>
+TB_HD void rows_to_cols(const uint32_t *w, uint32_t *col)
+{
+    using S = Shape<C, R>;
+    uint32_t lo[2][S::NB], hi[2][S::NB];
+#pragma unroll
+    for (int b = 0; b < S::NB; ++b) {
+        // block b = rows 8b..8b+7 = words 4b..4b+3; half 0 = columns 0-7, half 1 = columns 8-15
+        lo[0][b] = prmt(w[4 * b], w[4 * b + 1], 0x6420);
+        hi[0][b] = prmt(w[4 * b + 2], w[4 * b + 3], 0x6420);
+        transpose8(lo[0][b], hi[0][b]);
+        if (C > 8) {
+            lo[1][b] = prmt(w[4 * b], w[4 * b + 1], 0x7531);
+            hi[1][b] = prmt(w[4 * b + 2], w[4 * b + 3], 0x7531);
+            transpose8(lo[1][b], hi[1][b]);
+        }
+    }
+    // after the transpose byte j of (lo,hi) holds column j's bits for the block's 8 rows
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int half = c >> 3, j = c & 7;
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < S::NB; ++b) {
+            const uint32_t src = (j < 4) ? lo[half][b] : hi[half][b];
+            v |= ((src >> (8 * (j & 3))) & 0xffu) << (8 * b);
+        }
+        col[c] = v;
+    }
+}
+
+// column masks -> rows (packed words)
+template <int C, int R>
+TB_HD void cols_to_rows(const uint32_t *col, uint32_t *w)
+{
+    using S = Shape<C, R>;
+#pragma unroll
+    for (int b = 0; b < S::NB; ++b) {
+        uint32_t lo[2] = {0, 0}, hi[2] = {0, 0};
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int half = c >> 3, j = c & 7;
+            const uint32_t byte = (col[c] >> (8 * b)) & 0xffu;
+            if (j < 4) lo[half] |= byte << (8 * j); else hi[half] |= byte << (8 * (j - 4));
+        }
+        transpose8(lo[0], hi[0]);          // now byte i = row (8b+i) bits for columns 0-7
+        if (C > 8) transpose8(lo[1], hi[1]);
+        // word 4b+k holds rows 8b+2k (low half) and 8b+2k+1 (high half)
+        w[4 * b + 0] = prmt(lo[0], lo[1], 0x5140);
+        w[4 * b + 1] = prmt(lo[0], lo[1], 0x7362);
+        w[4 * b + 2] = prmt(hi[0], hi[1], 0x5140);
+        w[4 * b + 3] = prmt(hi[0], hi[1], 0x7362);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// from-scratch evaluation of the six board features (state.py:175-280), general form: valid for
+// any board with consistent heights, terminal or not (walls: all-ones mask, height R).
+// out6 = [rows_with_holes, column_transitions, holes, cumulative_wells, row_transitions, hole_depth]
+// ---------------------------------------------------------------------------------------------
+template <int C, int R>
+TB_HD void eval_full(const uint32_t *col, int *out6)
+{
+    using S = Shape<C, R>;
+    int holes = 0, ct = 0, hd = 0, wells = 0, rt = 0;
+    uint32_t hm = 0;
+    uint32_t L = S::ALL;
+    int hL = R;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const uint32_t x = col[c];
+        const int h = height_of(x);
+        const uint32_t Rt = (c + 1 < C) ? col[c + 1] : S::ALL;
+        const int hR = (c + 1 < C) ? height_of(col[c + 1]) : R;
+        const uint32_t mh = mask_lo(h);
+        const uint32_t hole = ~x & mh;
+        holes += popc32(hole);                                   // state.py:213
+        hm |= hole;                                              // :215
+        uint32_t t = hole & (x >> 1);                            // top cell of every vertical hole run
+        ct += 1 + 2 * popc32(t);                                 // :194,:219-220,:242-243
+        while (t) {                                              // :216 filled cells above the run
+            const int r = ctz32(t);
+            hd += popc32(x >> (r + 1));
+            t &= t - 1;
+        }
+        const int lim = imax(h, imin(hL, hR));                   // :258-260
+        wells += run_sum(L & Rt & ~x & mask_lo(lim));            // :222-233,:262-272
+        if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh); // :203-204,:225-226,:246-248
+        else rt += popc32(L & mask_lo(hL));                      // :254
+        L = x; hL = h;
+    }
+    rt += R - popc32(col[C - 1]);                                // :190 right wall
+    out6[0] = popc32(hm); out6[1] = ct; out6[2] = holes; out6[3] = wells; out6[4] = rt; out6[5] = hd;
+}
+
+// remove the rows in `full` from every column (rows above shift down): state.py:126-131
+template <int C>
+TB_HD void clear_rows(uint32_t *col, uint32_t full)
+{
+    while (full) {
+        const int r = 31 - clz32(full);                          // highest first: lower indices stay valid
+        const uint32_t lowm = mask_lo(r);
+#pragma unroll
+        for (int c = 0; c < C; ++c) col[c] = (col[c] & lowm) | ((col[c] >> 1) & ~lowm);
+        full &= ~(1u << r);
+    }
+}
+
+// Result of evaluating one placement.
+struct Eval {
+    float f[8];          // [rows_with_holes, column_transitions, holes, landing_height, cumulative_wells,
+                         //  row_transitions, eroded, hole_depth]  (game.py:10-18)
+    int a;               // anchor_row (pre-clear)
+    uint32_t full;       // cleared rows (absolute row mask)
+    int terminal;        // State.terminal_state
+};
+
+// hard-drop row of orientation `d` at column c given column heights h[0..C)
+TB_HD int anchor_row(uint32_t d, const int *h, int c)
+{
+    int a = 0;
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx)
+        if (desc_len(d, dx) > 0) a = imax(a, h[c + dx] - desc_bot(d, dx));
+    return a;
+}
+
+// Place orientation `d` at column c on `col` (in place), clear lines, report a/full/terminal.
+// Returns the number of piece cells in the cleared rows (for the eroded feature).
+template <int C, int R>
+TB_HD int place_and_clear(uint32_t *col, uint32_t d, int c, int &a_out, uint32_t &full_out, int &terminal)
+{
+    using S = Shape<C, R>;
+    int a = 0;
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx)
+        if (desc_len(d, dx) > 0) a = imax(a, height_of(col[imin(c + dx, C - 1)]) - desc_bot(d, dx));
+    uint32_t pm[4];
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) pm[dx] = mask_lo(desc_len(d, dx)) << (a + desc_bot(d, dx));
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const int dx = k - c;
+        if (dx >= 0 && dx < 4) col[k] |= pm[dx];
+    }
+    uint32_t full = S::ALL;
+#pragma unroll
+    for (int k = 0; k < C; ++k) full &= col[k];
+    full &= mask_lo(desc_chg(d)) << a;                           // only changed_lines are tested (state.py:122)
+    int cells = 0;
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) cells += popc32(pm[dx] & full);
+    if (full) clear_rows<C>(col, full);
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) any |= col[k];
+    terminal = (int)((any >> R) & 1u);                            // state.py:111-117
+    a_out = a; full_out = full;
+    return cells;
+}
+
+// Slow (general) path: build the afterstate board, clear, evaluate from scratch.
+// `col` is the current board (not modified unless out_col == col); out_col (nullable) gets the afterstate.
+template <int C, int R>
+TB_HD void eval_slow(const uint32_t *col, uint32_t d, int c, Eval &e, uint32_t *out_col)
+{
+    uint32_t nc[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) nc[k] = col[k];
+    const int cells = place_and_clear<C, R>(nc, d, c, e.a, e.full, e.terminal);
+    int six[6];
+    eval_full<C, R>(nc, six);
+    const int ncl = popc32(e.full);
+    e.f[0] = (float)six[0]; e.f[1] = (float)six[1]; e.f[2] = (float)six[2];
+    e.f[3] = (float)(2 * (e.a + 1) + desc_bonus2(d)) * 0.5f;      // state.py:102 (pre-clear anchor)
+    e.f[4] = (float)six[3]; e.f[5] = (float)six[4];
+    e.f[6] = (float)(cells * ncl);                               // state.py:99-101
+    e.f[7] = (float)six[5];
+    if (out_col) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) out_col[k] = nc[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-env record for incremental evaluation.  Built once per env (build_env), read by every
+// placement of that env (eval_fast).  Flat uint32 words so it can live in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int C, int R>
+struct Rec {
+    static constexpr int COLX = 0;                        // C+4 words: colx[k] = column k-2 (walls at -1, C)
+    static constexpr int PAND = COLX + C + 4;             // C+1 words: AND of columns < c
+    static constexpr int SAND = PAND + C + 1;             // C+1 words: AND of columns >= c
+    static constexpr int HPACK = SAND + C + 1;            // 2 words: 5-bit heights, entry k = column k-1
+    static constexpr int NRUNS = HPACK + 2;               // 2 words: 4-bit hole-run counts per column
+    static constexpr int PW = NRUNS + 2;                  // (C+1) u16: prefix sums of per-column wells
+    static constexpr int PRT = PW + (C + 2) / 2;          // (C+1) u16: prefix sums of per-column row transitions
+    static constexpr int TOT = PRT + (C + 2) / 2;         // ct, hd, wells, rt, holes, hole-row mask, hmax
+    static constexpr int T_CT = TOT + 0, T_HD = TOT + 1, T_WELLS = TOT + 2, T_RT = TOT + 3,
+                         T_HOLES = TOT + 4, T_HM = TOT + 5, T_HMAX = TOT + 6;
+    static constexpr int WORDS_RAW = TOT + 7;
+    static constexpr int WORDS = WORDS_RAW | 1;           // odd stride: conflict-free across envs
+};
+
+TB_HD uint32_t get_u16(const uint32_t *base, int i) { return (base[i >> 1] >> (16 * (i & 1))) & 0xffffu; }
+
+template <int C, int R>
+TB_HD void build_env(const uint32_t *col, uint32_t *rec)
+{
+    using S = Shape<C, R>;
+    using K = Rec<C, R>;
+    rec[K::COLX + 0] = 0u; rec[K::COLX + 1] = S::ALL;
+#pragma unroll
+    for (int c = 0; c < C; ++c) rec[K::COLX + 2 + c] = col[c];
+    rec[K::COLX + C + 2] = S::ALL; rec[K::COLX + C + 3] = 0u;
+    uint32_t acc = S::ALL;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { rec[K::PAND + c] = acc; acc &= col[c]; }
+    rec[K::PAND + C] = acc;
+    acc = S::ALL;
+    rec[K::SAND + C] = acc;
+#pragma unroll
+    for (int c = C - 1; c >= 0; --c) { acc &= col[c]; rec[K::SAND + c] = acc; }
+
+    uint64_t hp = (uint64_t)R, nrp = 0;
+    int holes = 0, ct = 0, hd = 0, wells = 0, rt = 0, hmax = 0;
+    uint32_t hm = 0, L = S::ALL;
+    int hL = R;
+    uint32_t pw[(C + 2) / 2], prt[(C + 2) / 2];
+#pragma unroll
+    for (int i = 0; i < (C + 2) / 2; ++i) { pw[i] = 0; prt[i] = 0; }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const uint32_t x = col[c];
+        const int h = height_of(x);
+        const uint32_t Rt = (c + 1 < C) ? col[c + 1] : S::ALL;
+        const int hR = (c + 1 < C) ? height_of(col[c + 1]) : R;
+        const uint32_t mh = mask_lo(h);
+        const uint32_t hole = ~x & mh;
+        holes += popc32(hole);
+        hm |= hole;
+        uint32_t t = hole & (x >> 1);
+        const int nr = popc32(t);
+        ct += 1 + 2 * nr;
+        while (t) { const int r = ctz32(t); hd += popc32(x >> (r + 1)); t &= t - 1; }
+        const int lim = imax(h, imin(hL, hR));
+        wells += run_sum(L & Rt & ~x & mask_lo(lim));
+        if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh);
+        else rt += popc32(L & mask_lo(hL));
+        hp |= (uint64_t)h << (5 * (c + 1));
+        nrp |= (uint64_t)nr << (4 * c);
+        pw[(c + 1) >> 1] |= (uint32_t)wells << (16 * ((c + 1) & 1));
+        prt[(c + 1) >> 1] |= (uint32_t)rt << (16 * ((c + 1) & 1));
+        hmax = imax(hmax, h);
+        L = x; hL = h;
+    }
+    hp |= (uint64_t)R << (5 * (C + 1));
+    rt += R - popc32(col[C - 1]);
+    rec[K::HPACK] = (uint32_t)hp; rec[K::HPACK + 1] = (uint32_t)(hp >> 32);
+    rec[K::NRUNS] = (uint32_t)nrp; rec[K::NRUNS + 1] = (uint32_t)(nrp >> 32);
+#pragma unroll
+    for (int i = 0; i < (C + 2) / 2; ++i) { rec[K::PW + i] = pw[i]; rec[K::PRT + i] = prt[i]; }
+    rec[K::T_CT] = (uint32_t)ct; rec[K::T_HD] = (uint32_t)hd; rec[K::T_WELLS] = (uint32_t)wells;
+    rec[K::T_RT] = (uint32_t)rt; rec[K::T_HOLES] = (uint32_t)holes; rec[K::T_HM] = hm;
+    rec[K::T_HMAX] = (uint32_t)hmax;
+}
+
+// Fast path: placement that clears no line and stays below the top.  Only the piece's columns and
+// their neighbours are re-evaluated; everything else comes from the env record.  Returns false when
+// the placement needs the general path (a line clears, or the piece reaches row R).
+// Precondition: every column height of the current board is <= R (a non-terminal state).
+template <int C, int R>
+TB_HD bool eval_fast(const uint32_t *rec, uint32_t d, int c, Eval &e)
+{
+    using S = Shape<C, R>;
+    using K = Rec<C, R>;
+    const int w = desc_w(d);
+    const uint64_t hp = (uint64_t)rec[K::HPACK] | ((uint64_t)rec[K::HPACK + 1] << 32);
+    const uint32_t hw = (uint32_t)(hp >> (5 * c));                 // entry k = height of column c-1+k
+    const uint64_t nrp = (uint64_t)rec[K::NRUNS] | ((uint64_t)rec[K::NRUNS + 1] << 32);
+    const uint32_t nrw = (uint32_t)(nrp >> (4 * c));               // entry dx = hole runs of column c+dx
+
+    int nh[6];                                                     // heights of columns c-1 .. c+4
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nh[k] = (int)((hw >> (5 * k)) & 31u);
+    int a = 0;
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx)
+        if (desc_len(d, dx) > 0) a = imax(a, nh[1 + dx] - desc_bot(d, dx));
+
+    uint32_t y[8];                                                 // columns c-2 .. c+5 after the placement
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = rec[K::COLX + c + k];
+    int gapsum = 0, gapcnt = 0, hdadd = 0, lastlen = 0;
+    uint32_t gapor = 0, fp = S::ALL;
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+        const int len = desc_len(d, dx);
+        if (len > 0) {
+            const int lo = a + desc_bot(d, dx);
+            const int g = lo - nh[1 + dx];                         // new holes under the piece in this column
+            y[2 + dx] |= mask_lo(len) << lo;
+            fp &= y[2 + dx];
+            gapsum += g;
+            gapcnt += (g > 0);
+            gapor |= mask_lo(lo) ^ mask_lo(nh[1 + dx]);
+            hdadd += len * ((int)((nrw >> (4 * dx)) & 15u) + (g > 0));
+            nh[1 + dx] = lo + len;
+            lastlen = len;
+        }
+    }
+    const uint32_t full = rec[K::PAND + c] & rec[K::SAND + c + w] & fp & (mask_lo(desc_chg(d)) << a);
+    if (full != 0u || a + desc_ph(d) > R) return false;
+
+    // wells over columns c-1 .. c+4, row transitions over columns c .. c+4 (clipped to the board)
+    const int wlo = imax(c - 1, 0), hi = imin(c + 4, C - 1);
+    int wells = (int)rec[K::T_WELLS] - (int)(get_u16(rec + K::PW, hi + 1) - get_u16(rec + K::PW, wlo));
+    int rt = (int)rec[K::T_RT] - (int)(get_u16(rec + K::PRT, hi + 1) - get_u16(rec + K::PRT, c));
+#pragma unroll
+    for (int k = 1; k <= 6; ++k) {
+        const int j = c - 2 + k;
+        if (j >= 0 && j < C) wells += run_sum(y[k - 1] & y[k + 1] & ~y[k]);
+    }
+#pragma unroll
+    for (int k = 2; k <= 6; ++k) {
+        const int j = c - 2 + k;
+        if (j < C) {
+            const int hj = nh[k - 1], hl = nh[k - 2];
+            if (hj > 0) rt += imax(0, hl - hj) + popc32((y[k] ^ y[k - 1]) & mask_lo(hj));
+            else rt += popc32(y[k - 1]);                           // left neighbour is a real column here
+        }
+    }
+    if (c + w == C) rt -= lastlen;                                 // right-wall term R - popc(col[C-1])
+
+    e.a = a; e.full = 0u; e.terminal = 0;
+    e.f[0] = (float)popc32(rec[K::T_HM] | gapor);
+    e.f[1] = (float)((int)rec[K::T_CT] + 2 * gapcnt);
+    e.f[2] = (float)((int)rec[K::T_HOLES] + gapsum);
+    e.f[3] = (float)(2 * (a + 1) + desc_bonus2(d)) * 0.5f;
+    e.f[4] = (float)wells;
+    e.f[5] = (float)rt;
+    e.f[6] = 0.0f;
+    e.f[7] = (float)((int)rec[K::T_HD] + hdadd);
+    return true;
+}
+
+// Tetris.fitness (game.py:109-120): float32 products and sums, left to right, no FMA contraction.
+TB_HD float fitness(const float *f, const float *w)
+{
+#if defined(__CUDA_ARCH__)
+    float acc = __fmul_rn(f[0], w[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) acc = __fadd_rn(acc, __fmul_rn(f[i], w[i]));
+    return acc;
+#else
+    volatile float acc = f[0] * w[0];
+    for (int i = 1; i < 8; ++i) { volatile float p = f[i] * w[i]; acc = acc + p; }
+    return acc;
+#endif
+}
+
+// Is the placement a legal action, i.e. a non-terminal afterstate (game.py:69)?  Cheap in the common
+// case (heights only); falls back to an exact place-and-clear when the piece reaches row R.
+template <int C, int R>
+TB_HD bool placement_valid(const uint32_t *col, const int *h, uint32_t d, int c)
+{
+    const int a = anchor_row(d, h, c);
+    if (a + desc_ph(d) <= R) return true;
+    uint32_t nc[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) nc[k] = col[k];
+    int aa, term; uint32_t full;
+    place_and_clear<C, R>(nc, d, c, aa, full, term);
+    return term == 0;
+}
+
+}  // namespace tb
