@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- placements/sec of the batched Tetris environment (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference on host cores
+
+Workload (config.workload): BASELINE.json configs[3]'s per-GPU shard -- 2^20 envs per GPU, 10x20 board, 7-piece
+set, greedy linear policy with the BCTS weights of game.py:111-118, game-over detection + auto-reset, synthetic
+(seeded, in-kernel RNG) piece streams.  A "step" is one fused rollout launch of `rollout_steps` placements for every
+env (= example_play.py:11-21 loop bodies) followed, for N > 1, by the NCCL all-reduce of the episode statistics.
+Weak scaling: envs per GPU fixed, env ids global (rank r owns [r*E, (r+1)*E)), no per-step communication.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C, R, PIECE_SET = 10, 20, 1
+STATE_READ_BYTES = 64          # 3 x 128-bit row planes + 128-bit meta per env (include/tetris_b200.h)
+METRIC = "placements/sec (env steps/sec), greedy-linear policy, whole job"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--rollout-steps", type=int, default=32, help="placements per env per step")
+    ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu baseline / e2e side measurements")
+    return ap.parse_args()
+
+
+def config_of(args, n_gpus):
+    return {
+        "workload": "BASELINE configs[3] per-GPU shard: greedy linear policy (BCTS weights, game.py:111-118) playing "
+                    "with game-over + auto-reset, 10x20 board, 7-piece set; %d envs/GPU x %d placements per step"
+                    % (args.envs, args.rollout_steps),
+        "board": "10x20", "piece_set": "7-piece (game.py:41-47)", "policy": "greedy-linear BCTS",
+        "envs_per_gpu": args.envs, "total_envs": args.envs * n_gpus, "rollout_steps": args.rollout_steps,
+        "l2": "flushed between timed steps (256 MiB write outside the timed events)",
+        "parallelism": "envs sharded over %d GPU(s); stats all-reduce only" % n_gpus,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_rate(seconds_target, threads, policy=1, seed=1):
+    """The oracle port of the reference's loop on `threads` host cores; returns (placements/s, afterstates/s, sample)."""
+    from oracle import oracle as orc
+    n_env = 256 * threads
+    b = orc.Batch(C, R, n_env, piece_set=PIECE_SET, seed=seed)
+    b.reset()
+    b.rollout(30, 0, threads=threads)                       # realistic boards, untimed
+    t0 = time.perf_counter()
+    st = b.rollout(4, policy, threads=threads)
+    probe = time.perf_counter() - t0
+    rate = n_env * 4 / max(probe, 1e-6)
+    T = max(4, int(seconds_target * rate / n_env))
+    t0 = time.perf_counter()
+    st = b.rollout(T, policy, threads=threads)
+    dt = time.perf_counter() - t0
+    sample = "%d envs x %d placements (greedy BCTS, 10x20, 7-piece) in %.1f s on %d threads" % (n_env, T, dt, threads)
+    return n_env * T / dt, float(st[4]) / dt, sample
+
+
+def run_reference(args):
+    """CPU arm.  The reference is pure Python and cannot travel to the GPU box (/root/reference is absent there), so
+    this times the oracle's C port of its loop (oracle/tetris_oracle.c, pinned to the reference by golden fixtures)
+    on every host core.  Each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    threads = os.cpu_count() or 1
+    n_env = 512 * threads
+    T = args.rollout_steps
+    b = orc.Batch(C, R, n_env, piece_set=PIECE_SET, seed=args.seed)
+    b.reset()
+    b.rollout(30, 0, threads=threads)
+    for _ in range(args.warmup):
+        b.rollout(T, 1, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.rollout(T, 1, threads=threads)
+    dt = time.perf_counter() - t0
+    value = n_env * T * args.steps / dt
+    sample = "%d envs x %d placements per step on %d host threads (C port of the reference loop)" % (n_env, T, threads)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards / f32 features",
+        "data": "synthetic", "config": config_of(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "placements/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tetris_b200 import BCTS_WEIGHTS, BatchedTetris, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU product path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W, T, E = args.steps, args.warmup, args.rollout_steps, args.envs
+    W = max(W, 3)
+
+    env = BatchedTetris(C, R, E, piece_set=PIECE_SET, seed=args.seed, env_offset=rank * E, device=dev)
+    env.rollout(30, "random")                                # realistic, de-synchronised boards (untimed)
+    env.stats.zero_()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    weights = np.asarray(BCTS_WEIGHTS, np.float32)
+
+    def step():
+        env.rollout(T, "greedy", weights)
+        if world > 1:
+            red = env.stats.clone()                          # end-of-rollout reduction of episode statistics
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)
+            return red
+        return env.stats
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        step()
+        e.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    ms = sum(s.elapsed_time(e) for s, e in ev)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    placements = float(world) * E * T * K
+    value = placements / (ms * 1e-3)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 bitboards / f32 features", "data": "synthetic", "config": config_of(args, world),
+        "clocks": clocks, "gpu_launches": K, "wall_s_timed_region": wall,
+    }
+
+    if rank == 0 and not args.no_extras:
+        stats = env.stats_dict()
+        out["rollout_afterstates_per_s_per_gpu"] = None
+        # afterstates evaluated inside the timed rollouts (this rank): measured, not estimated
+        torch.cuda.synchronize()
+        a0 = env.stats_dict()["afterstates"]
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); env.rollout(T, "greedy", weights); e.record(); torch.cuda.synchronize()
+        out["rollout_afterstates_per_s_per_gpu"] = (env.stats_dict()["afterstates"] - a0) / (s.elapsed_time(e) * 1e-3)
+        out["episode_stats_rank0"] = {k: stats[k] for k in ("placements", "episodes", "lines", "max_ep_lines")}
+
+        # ---- roofline of the afterstate kernel (K1, the north_star's roofline target), timed live
+        feats = torch.empty((E, env.a_max, 8), dtype=torch.float32, device=dev)
+        valid = torch.empty(E, dtype=torch.int64, device=dev)
+        count = torch.empty(E, dtype=torch.int32, device=dev)
+        for _ in range(3):
+            env.get_after_states(out=(feats, valid, count))
+        torch.cuda.synchronize()
+        k1 = []
+        for _ in range(5):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); env.get_after_states(out=(feats, valid, count)); e.record()
+            torch.cuda.synchronize()
+            k1.append(s.elapsed_time(e))
+        k1_ms = sum(k1) / len(k1)
+        n_slots = torch.as_tensor([_lib.lib().tb_num_slots(p, C) for p in range(9)], device=dev)
+        slots_total = int(n_slots[env.export_boards()[2].long()].sum().item())
+        alg_bytes = E * (STATE_READ_BYTES + 12) + 32 * slots_total      # state read + mask/count + 32 B per afterstate
+        peak, peak_src = measured_peak_gbs()
+        achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+        out["roofline"] = {
+            "kernel": "k_afterstates<10,20> (K1: enumerate + 8 features for every placement of 2^20 envs)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "ms_per_launch": k1_ms, "afterstates_per_s": slots_total / (k1_ms * 1e-3),
+            "note": "integer-issue-bound kernel: see profiles/ for the ncu pipe utilisation; traffic from ncu --set full",
+        }
+        del feats
+
+        # ---- e2e through the public API with host buffers: weights from the host, statistics read back every step
+        host_stats = torch.empty(len(_lib.STATS), dtype=torch.int64).pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            w_host = np.array(BCTS_WEIGHTS, np.float32)                 # step input: 8 floats from the host
+            env.rollout(T, "greedy", w_host)
+            host_stats.copy_(env.stats, non_blocking=True)
+            torch.cuda.synchronize()                                   # the caller reads the result
+        e2e_dt = time.perf_counter() - t0
+        out["e2e"] = {"value": E * T * K / e2e_dt, "unit": "placements/s", "h2d_bytes_per_step": 32,
+                      "d2h_bytes_per_step": 8 * len(_lib.STATS),
+                      "note": "BatchedTetris.rollout(): policy weights in, episode statistics out, per rank"}
+
+        # ---- e2e of the lockstep API a host-side policy uses: features to the host, actions back (PCIe-bound)
+        try:
+            nl = min(E, 1 << 18)
+            env2 = BatchedTetris(C, R, nl, piece_set=PIECE_SET, seed=args.seed + 1, device=dev)
+            env2.rollout(20, "random")
+            hf = torch.empty((nl, env2.a_max, 8), dtype=torch.float32).pin_memory()
+            hc = torch.empty(nl, dtype=torch.int32).pin_memory()
+            ha = torch.zeros(nl, dtype=torch.int32).pin_memory()
+            ho = torch.empty((nl, 8), dtype=torch.float32).pin_memory()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_it = 3
+            for _ in range(n_it):
+                f, v, c = env2.get_after_states()
+                hf.copy_(f, non_blocking=True); hc.copy_(c, non_blocking=True)
+                torch.cuda.synchronize()
+                obs, rew, done, lines = env2.step(ha.to(dev, non_blocking=True), auto_reset=True, check=False)
+                ho.copy_(obs, non_blocking=True)
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out["e2e_lockstep_host_policy"] = {
+                "value": nl * n_it / dt, "unit": "placements/s", "envs": nl,
+                "h2d_bytes_per_step": 4 * nl, "d2h_bytes_per_step": nl * (env2.a_max * 32 + 4 + 32),
+                "note": "get_after_states -> features D2H -> actions H2D -> step -> obs D2H (action 0 for all envs)"}
+            del env2
+        except Exception as ex:                                        # side measurement only
+            out["e2e_lockstep_host_policy"] = {"error": repr(ex)}
+
+        # ---- random policy and the 4096-env lockstep config, for context
+        try:
+            envr = BatchedTetris(C, R, E, piece_set=PIECE_SET, seed=args.seed + 2, device=dev)
+            envr.rollout(30, "random")
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); envr.rollout(64, "random"); e.record(); torch.cuda.synchronize()
+            out["random_policy_placements_per_s_per_gpu"] = E * 64 / (s.elapsed_time(e) * 1e-3)
+            del envr
+            env4 = BatchedTetris(C, R, 4096, piece_set=PIECE_SET, seed=args.seed, device=dev)
+            g = torch.Generator(device=dev); g.manual_seed(0)
+            for it in range(60):
+                if it == 10:
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                f, v, c = env4.get_after_states()
+                a = (torch.randint(0, 2 ** 31 - 1, (4096,), device=dev, generator=g) % c.long()).int()
+                env4.step(a, auto_reset=True, check=False)
+            torch.cuda.synchronize()
+            out["lockstep_4096_placements_per_s"] = 4096 * 50 / (time.perf_counter() - t0)
+        except Exception as ex:
+            out["random_policy_placements_per_s_per_gpu"] = repr(ex)
+
+        # ---- CPU baseline beside it (N = 1 only): the oracle port on this box's host cores
+        if world == 1:
+            threads = os.cpu_count() or 1
+            v, av, sample = cpu_port_rate(12.0, threads)
+            out["cpu_baseline"] = {"value": v, "unit": "placements/s", "cores": threads, "kind": "port",
+                                   "sample": sample, "afterstates_per_s": av}
+
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

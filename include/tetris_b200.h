@@ -1,0 +1,161 @@
+/*
+ * tetris_b200.h -- C ABI of the B200-native batched Tetris environment.
+ *
+ * The reference (s0phia-/tetris) has no FFI layer: its boundary is the Python surface of
+ * game.py / state.py / tetromino.py.  The Python package in this repo (tetris_b200.game.Tetris,
+ * tetris_b200.batched.BatchedTetris, re-exported as package `tetris`) mirrors that surface and
+ * binds the entry points below through ctypes; each entry point names the reference code it
+ * replaces (file:line into the reference checkout).
+ *
+ * Conventions:
+ *   - extern "C", plain pointers and sizes only; no C++ or torch types.
+ *   - every call returns 0 on success, <0 on error; tb_last_error() gives the message
+ *     (thread-local).  Nothing throws across the ABI.
+ *   - all buffers are caller-owned DEVICE memory unless a parameter says "host"; nothing is
+ *     allocated inside; launches are asynchronous on the caller's cudaStream_t (`stream`).
+ *   - no global mutable state besides per-device __constant__ tables: safe from several host
+ *     threads on distinct streams / devices.
+ *   - board shape (num_columns C, num_rows R) selects a compiled template instantiation;
+ *     tb_supported_shape() says which exist (10x20, 10x10, 6x12, 8x16, 4x4 ... see tb_kernels.cu).
+ *
+ * Device state ("state" below) is one caller-owned allocation of tb_state_bytes() bytes, 256-byte
+ * aligned, laid out as a structure of arrays over envs:
+ *   planes  uint4[NB][n_env]   row masks, uint16 per row (bit c = cell (r, c)), 8 rows per 128-bit word,
+ *                              NB = ceil((R + 4) / 8)
+ *   meta    uint4[n_env]       bytes 0..9 column heights (lowest_free_rows, state.py:162-172),
+ *                              byte 10 current piece (global id), byte 11 bag mask, bytes 12..15 draw counter
+ *   epi     uint2[n_env]       placements and lines of the running episode
+ *
+ * Piece ids (global): 0 Straight, 1 RCorner, 2 LCorner, 3 Square, 4 SnakeR, 5 SnakeL, 6 T   (game.py:41-47)
+ *                     7 ThreeL, 8 ThreeLine                                               (game.py:38-39)
+ * Piece sets: 0 = reference default {ThreeL, ThreeLine}; 1 = the seven tetrominoes.
+ * Afterstate slots are in the reference's enumeration (= action) order, tetromino.py:*.get_after_states.
+ * Feature order (game.py:10-18): rows_with_holes, column_transitions, holes, landing_height,
+ *                                cumulative_wells, row_transitions, eroded, hole_depth.
+ */
+#ifndef TETRIS_B200_H
+#define TETRIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_VERSION 100          /* 0.1.0 */
+#define TB_NUM_FEATURES 8
+#define TB_MAX_SLOTS 36         /* ThreeL at C = 10 */
+
+/* tb_step / tb_afterstates flags */
+#define TB_FLAG_AUTO_RESET     1   /* step: reset a finished env in place (what example_play.py:20-21 does) */
+#define TB_FLAG_ACTION_IS_SLOT 2   /* step: actions index enumeration slots instead of non-terminal ranks   */
+
+/* tb_rollout policies */
+#define TB_POLICY_RANDOM 0         /* uniformly random legal placement (per-env counter RNG, stream 1)       */
+#define TB_POLICY_GREEDY 1         /* first arg-max of the float32 linear score over legal afterstates
+                                      (Tetris.fitness, game.py:109-120)                                      */
+
+/* tb_rollout statistics, int64 each; sums except the two maxima */
+enum {
+    TB_ST_PLACEMENTS = 0, TB_ST_EPISODES, TB_ST_LINES, TB_ST_REWARD, TB_ST_AFTERSTATES,
+    TB_ST_LINES0, TB_ST_LINES1, TB_ST_LINES2, TB_ST_LINES3, TB_ST_LINES4,
+    TB_ST_MAX_EP_LINES, TB_ST_MAX_EP_STEPS, TB_ST_SUM_EP_STEPS, TB_ST_SUM_EP_LINES,
+    TB_ST_RESERVED0, TB_ST_RESERVED1, TB_ST_COUNT
+};
+
+int tb_version(void);
+const char *tb_last_error(void);
+
+/* 1 if kernels for this board shape were compiled in. */
+int tb_supported_shape(int num_columns, int num_rows);
+/* Bytes of device state for n_env envs (0 if the shape is unsupported). */
+size_t tb_state_bytes(int num_columns, int num_rows, int64_t n_env);
+/* Number of afterstates (enumeration slots) of a piece: SURVEY.md Appendix A. */
+int tb_num_slots(int piece, int num_columns);
+/* max over the set's pieces = row stride callers should use for per-slot outputs. */
+int tb_a_max(int num_columns, int piece_set);
+
+/*
+ * Tetris.__init__ + reset (game.py:21-63): empty boards, fresh bags, zero counters, draw the first piece.
+ *   env_offset  global id of env 0 of this shard (per-env RNG is keyed by seed and GLOBAL env id, so results do
+ *               not depend on how envs are sharded over GPUs)
+ *   piece_tape  nullable uint8[n_env]: global piece ids to use instead of the bag RNG (parity runs)
+ *   reset_mask  nullable uint8[n_env]: if given, behaves like Tetris.reset() (game.py:53-63) on the flagged
+ *               envs only -- board emptied, one more piece drawn, the bag persists
+ */
+int tb_reset(void *state, int num_columns, int num_rows, int64_t n_env, int64_t env_offset, uint64_t seed,
+             int piece_set, const uint8_t *piece_tape, const uint8_t *reset_mask, void *stream);
+
+/*
+ * Tetris.get_after_states(include_terminal=True) (game.py:67-80) for every env: enumerate every
+ * rotation x column placement of the current piece (tetromino.py:*.get_after_states), drop, lock, clear
+ * (state.py:121-143), terminal test (state.py:111-117) and the eight BCTS features (state.py:97-107,175-280).
+ *   feats_out   float32[n_env][a_stride][8], by enumeration slot (rows >= tb_num_slots(piece) are not written)
+ *   valid_out   uint64[n_env]: bit s set  <=>  slot s is a non-terminal afterstate (a legal action)
+ *   count_out   int32[n_env]: number of legal actions (len(self.afterstates), game.py:69)
+ *   directions  nullable HOST float[8]: per-feature multipliers (feature_directions, state.py:49-50), applied in fp32
+ */
+int tb_afterstates(const void *state, int num_columns, int num_rows, int64_t n_env, float *feats_out,
+                   uint64_t *valid_out, int32_t *count_out, int a_stride, const float *directions, void *stream);
+
+/*
+ * Afterstates with their boards, for the single-env State objects of the compatibility layer
+ * (tetromino.py builds a State per afterstate, state.py:5-38).  All outputs nullable.
+ *   rows_out    uint16[n_env][a_stride][R+4]   board after clearing
+ *   heights_out uint8 [n_env][a_stride][C]     lowest_free_rows after clearing
+ *   info_out    int32 [n_env][a_stride][4]     anchor_row, cleared-row mask (absolute rows), terminal, anchor_col
+ */
+int tb_afterstates_export(const void *state, int num_columns, int num_rows, int64_t n_env, float *feats_out,
+                          uint16_t *rows_out, uint8_t *heights_out, int32_t *info_out, int a_stride, void *stream);
+
+/*
+ * Tetris.step (game.py:82-92) + is_game_over (game.py:94-100) for every env.
+ *   actions     int32[n_env]: index into the non-terminal afterstates (game.py:69,83), or an enumeration slot
+ *               with TB_FLAG_ACTION_IS_SLOT
+ *   piece_tape  nullable uint8[n_env]: next piece per env (global id) instead of the bag RNG
+ *   obs_out     nullable float32[n_env][8]: features of the chosen afterstate (game.py:91)
+ *   reward_out  nullable int32[n_env]: lines - 1, and -100 more when done (game.py:86-90)
+ *   done_out    nullable uint8[n_env]; lines_out nullable int32[n_env]
+ *   status_out  nullable int32[1]: set non-zero if any action was out of range (the reference raises IndexError,
+ *               game.py:83); such envs are left untouched
+ */
+int tb_step(void *state, int num_columns, int num_rows, int64_t n_env, int64_t env_offset, uint64_t seed,
+            int piece_set, const int32_t *actions, const uint8_t *piece_tape, float *obs_out, int32_t *reward_out,
+            uint8_t *done_out, int32_t *lines_out, int32_t *status_out, int flags, void *stream);
+
+/*
+ * The example_play.py:11-21 loop fused on the device: n_steps placements per env with an in-kernel policy,
+ * game-over detection and auto-reset; episode statistics are ADDED into stats (max for the two maxima).
+ *   weights     HOST float[8] for TB_POLICY_GREEDY (game.py:111-118 gives the BCTS weights); ignored for random
+ *   stats       int64[TB_ST_COUNT] device
+ */
+int tb_rollout(void *state, int num_columns, int num_rows, int64_t n_env, int64_t env_offset, uint64_t seed,
+               int piece_set, int n_steps, int policy, const float *weights, int64_t *stats, void *stream);
+
+/*
+ * State interchange (state.py:22-25,162-172; utils.py:179-191 needs the board on the host).
+ * export: rows_out uint16[count][R+4], heights_out uint8[count][C], piece_out uint8[count] (all nullable)
+ * import: rows_in  uint16[count][R+4] (heights are recomputed), piece_in nullable uint8[count]
+ */
+int tb_export_boards(const void *state, int num_columns, int num_rows, int64_t n_env, int64_t first, int64_t count,
+                     uint16_t *rows_out, uint8_t *heights_out, uint8_t *piece_out, void *stream);
+int tb_import_boards(void *state, int num_columns, int num_rows, int64_t n_env, int64_t first, int64_t count,
+                     const uint16_t *rows_in, const uint8_t *piece_in, void *stream);
+
+/*
+ * State.__init__ + get_features on caller-supplied boards (state.py:5-38,97-107): clear the full rows among
+ * changed_lines, recompute heights, terminal test, features.
+ *   rows_in     uint16[n][R+4]
+ *   params      int32[n][4]: anchor_row (changed_lines[0]), len(changed_lines) (1..4),
+ *               pieces_per_changed_row packed 4 bits each, 2 * landing_height_bonus
+ *   rows_out uint16[n][R+4], heights_out uint8[n][C], info_out int32[n][4] = (n_cleared, cleared-row mask,
+ *   terminal, 0), feats_out float32[n][8]      (all nullable)
+ */
+int tb_eval_states(int num_columns, int num_rows, int64_t n, const uint16_t *rows_in, const int32_t *params,
+                   uint16_t *rows_out, uint8_t *heights_out, int32_t *info_out, float *feats_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETRIS_B200_H */

@@ -43,9 +43,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
         cols_to_rows<C, R>(nc, wo);
         for (int r = 0; r < S::N; ++r) rows_out[s * S::N + r] = (uint16_t)(wo[r >> 1] >> (16 * (r & 1)));
         // placement_valid must agree with the terminal flag
-        int h[C];
-        for (int k = 0; k < C; ++k) h[k] = height_of(col[k]);
-        if (placement_valid<C, R>(col, h, d, c) != (e.terminal == 0)) return -1;
+        if (placement_valid<C, R>(col, d, c) != (e.terminal == 0)) return -1;
     }
     return n;
 }

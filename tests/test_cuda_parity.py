@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via tetris_b200.BatchedTetris) against the golden
+fixtures recorded from the reference and against the CPU oracle on the same seeded inputs.  Bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from golden_util import TRACES, feat2, load, rep_to_rows, rows_to_rep
+from test_oracle_golden import replay_trace
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(10, 20), (10, 10), (6, 12), (8, 16), (4, 4)]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class CudaBatch:
+    """tetris_b200.BatchedTetris behind the oracle.Batch interface the trace replayer drives."""
+
+    def __init__(self, Cc, R, n, piece_set=1, seed=0, env_offset=0):
+        from tetris_b200 import BatchedTetris, _lib
+        self.env = BatchedTetris(Cc, R, n, piece_set=piece_set, seed=seed, env_offset=env_offset)
+        self.n, self.C, self.R = n, Cc, R
+        self._lib = _lib.lib()
+
+    @property
+    def piece(self):
+        return self.env.piece.astype(np.int32)
+
+    @property
+    def heights(self):
+        return self.env.heights.astype(np.int32)
+
+    def rows(self):
+        return self.env.rows()
+
+    def reset(self, tape=None):
+        self.env.reset(tape)
+
+    def reset_masked(self, mask, tape=None):
+        self.env.reset_masked(np.asarray(mask, np.uint8), tape)
+
+    def afterstates(self):
+        feats, valid, count = self.env.get_after_states()
+        n_all = np.array([self._lib.tb_num_slots(int(p), self.C) for p in self.piece], np.int32)
+        f = feats.cpu().numpy()
+        for e in range(self.n):
+            f[e, n_all[e]:] = 0
+        return f, valid.cpu().numpy().view(np.uint64), count.cpu().numpy(), n_all
+
+    def step(self, actions, tape=None, auto_reset=False, action_is_slot=False):
+        obs, reward, done, lines = self.env.step(actions, tape=tape, auto_reset=auto_reset,
+                                                 action_is_slot=action_is_slot)
+        return obs.cpu().numpy(), reward.cpu().numpy(), done.cpu().numpy(), lines.cpu().numpy()
+
+
+def _cuda_batch(Cc, R, n, ps, seed):
+    return CudaBatch(Cc, R, n, ps, seed)
+
+
+def test_library_loaded():
+    from tetris_b200 import _lib
+    assert _lib.lib().tb_version() >= 100
+
+
+@pytest.mark.parametrize("name", TRACES)
+def test_trace_tape(name):
+    replay_trace(load("trace_" + name), _cuda_batch, rng_mode=False)
+
+
+@pytest.mark.parametrize("name", TRACES)
+def test_trace_rng(name):
+    replay_trace(load("trace_" + name), _cuda_batch, rng_mode=True)
+
+
+def test_afterstates_fixture():
+    """Every board x piece of the reference-generated fixture, through tb_afterstates and tb_afterstates_export."""
+    torch = _torch()
+    from tetris_b200 import BatchedTetris, _lib
+    g = load("afterstates")
+    shapes = g["shape"].astype(int)
+    for (Cc, R) in ((10, 20), (10, 10), (6, 12)):
+        idx = np.nonzero((shapes[:, 0] == Cc) & (shapes[:, 1] == R))[0]
+        N = R + 4
+        for ps in (0, 1):
+            sel = np.array([i for i in idx if (g["piece"][i] >= 7) == (ps == 0)])
+            env = BatchedTetris(Cc, R, len(sel), piece_set=ps)
+            env.import_boards(g["rows"][sel][:, :N], piece=g["piece"][sel].astype(np.uint8))
+            feats, valid, count = env.get_after_states()
+            feats, valid, count = feats.cpu().numpy(), valid.cpu().numpy(), count.cpu().numpy()
+            A = env.a_max
+            rows_o = torch.empty((len(sel), A, N), dtype=torch.int16, device="cuda")
+            h_o = torch.empty((len(sel), A, Cc), dtype=torch.uint8, device="cuda")
+            info_o = torch.empty((len(sel), A, 4), dtype=torch.int32, device="cuda")
+            f_o = torch.empty((len(sel), A, 8), dtype=torch.float32, device="cuda")
+            p = lambda t: C.c_void_p(t.data_ptr())
+            _lib.check(_lib.lib().tb_afterstates_export(C.c_void_p(env.state.data_ptr()), Cc, R, len(sel), p(f_o),
+                                                        p(rows_o), p(h_o), p(info_o), A, None))
+            torch.cuda.synchronize()
+            rows_o = rows_o.cpu().numpy().view(np.uint16)
+            h_o, info_o, f_o = h_o.cpu().numpy(), info_o.cpu().numpy(), f_o.cpu().numpy()
+            for k, i in enumerate(sel):
+                s, n = int(g["start"][i]), int(g["count"][i])
+                sl = slice(s, s + n)
+                assert np.array_equal(feat2(feats[k, :n]), g["a_feat2"][sl]), (Cc, R, i)
+                assert np.array_equal(feat2(f_o[k, :n]), g["a_feat2"][sl])
+                term = g["a_terminal"][sl]
+                vb = ((int(valid[k]) >> np.arange(n)) & 1).astype(bool)
+                assert np.array_equal(vb, ~term)
+                assert count[k] == (~term).sum()
+                assert np.array_equal(rows_o[k, :n], g["a_rows"][sl][:, :N])
+                assert np.array_equal(h_o[k, :n], g["a_heights"][sl][:, :Cc])
+                assert np.array_equal(info_o[k, :n, 0], g["a_anchor"][sl][:, 1])
+                assert np.array_equal(info_o[k, :n, 3], g["a_anchor"][sl][:, 0])
+                assert np.array_equal(info_o[k, :n, 2].astype(bool), term)
+                ncl = np.array([bin(int(m) & 0xffffffff).count("1") for m in info_o[k, :n, 1]])
+                assert np.array_equal(ncl, g["a_n_cleared"][sl])
+
+
+def _sync_oracle_from_device(env, ob):
+    """Copy the device envs' boards/pieces into an oracle batch."""
+    rows, heights, piece = env.export_boards()
+    ob.rep[:] = rows_to_rep(rows.cpu().numpy().view(np.uint16), env.num_columns)
+    ob.heights[:] = heights.cpu().numpy()
+    ob.piece[:] = piece.cpu().numpy()
+
+
+def _compare_state(env, ob):
+    assert np.array_equal(env.rows(), ob.rows())
+    assert np.array_equal(env.heights, ob.heights)
+    assert np.array_equal(env.piece, ob.piece)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("piece_set", [0, 1])
+def test_lockstep_vs_oracle(shape, piece_set):
+    """BASELINE config 2: 4096 lockstep envs, random legal placements, device RNG, compared with the oracle after
+    every step (boards, heights, pieces, legal counts, feature matrices, obs, reward, done, lines)."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    Cc, R = shape
+    n = 4096 if shape == (10, 20) else 1024
+    steps = 200 if shape == (10, 20) else 80
+    seed = 0x5EED
+    env = BatchedTetris(Cc, R, n, piece_set=piece_set, seed=seed)
+    ob = orc.Batch(Cc, R, n, piece_set=piece_set, seed=seed)
+    ob.reset()
+    _compare_state(env, ob)
+    u = np.random.RandomState(0).randint(0, 2 ** 31 - 1, size=(steps, n))
+    n_done = 0
+    for t in range(steps):
+        feats, valid, count = env.get_after_states()
+        of, ov, oc, on = ob.afterstates()
+        assert np.array_equal(count.cpu().numpy(), oc), t
+        assert np.array_equal(valid.cpu().numpy().view(np.uint64), ov), t
+        f = feats.cpu().numpy()
+        mask = np.arange(env.a_max)[None, :] < on[:, None]
+        assert np.array_equal(f[mask], of[mask]), t
+        a = (u[t] % oc).astype(np.int32)
+        obs, rew, done, lines = env.step(a, auto_reset=True)
+        oobs, orew, odone, olines = ob.step(a, auto_reset=True)
+        assert np.array_equal(obs.cpu().numpy(), oobs), t
+        assert np.array_equal(rew.cpu().numpy(), orew), t
+        assert np.array_equal(done.cpu().numpy(), odone), t
+        assert np.array_equal(lines.cpu().numpy(), olines), t
+        _compare_state(env, ob)
+        n_done += int(odone.sum())
+    assert n_done > 0
+
+
+@pytest.mark.parametrize("policy", ["random", "greedy"])
+@pytest.mark.parametrize("shape", [(10, 20), (10, 10), (6, 12), (4, 4)])
+def test_rollout_vs_oracle(shape, policy):
+    """Fused rollout kernels (in-kernel policy, RNG, game-over, auto-reset) against the oracle's loop: identical
+    final boards/pieces/counters and identical episode statistics."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    Cc, R = shape
+    n, seed = 2048 + 17, 77            # not a multiple of 32: exercises the ragged last warp tile
+    T = 40 if policy == "random" else 25
+    env = BatchedTetris(Cc, R, n, piece_set=1, seed=seed, env_offset=5)
+    ob = orc.Batch(Cc, R, n, piece_set=1, seed=seed, env_offset=5)
+    ob.reset()
+    total = np.zeros(16, np.int64)
+    for rnd in range(3):
+        env.rollout(T, policy)
+        st = ob.rollout(T, 0 if policy == "random" else 1, threads=8)
+        mx = np.maximum(total[10:12], st[10:12])
+        total += st
+        total[10:12] = mx                                  # the two maxima combine by max, the rest by sum
+        _compare_state(env, ob)
+        assert np.array_equal(env.stats.cpu().numpy(), total), rnd
+    assert total[0] == 3 * T * n and total[1] > 0
+
+
+def test_sharding_invariance():
+    """per-env RNG is keyed by the GLOBAL env id, so splitting the env range into shards (as the
+    multi-GPU launcher does) leaves every env's trajectory and the summed statistics unchanged."""
+    from tetris_b200 import BatchedTetris
+    n, seed, T = 3000, 5, 30
+    whole = BatchedTetris(10, 10, n, piece_set=1, seed=seed)
+    whole.rollout(T, "greedy")
+    whole.rollout(T, "random")
+    parts, off = [], 0
+    for cnt in (1000, 1500, 500):
+        p = BatchedTetris(10, 10, cnt, piece_set=1, seed=seed, env_offset=off)
+        p.rollout(T, "greedy")
+        p.rollout(T, "random")
+        parts.append(p)
+        off += cnt
+    assert np.array_equal(np.concatenate([p.rows() for p in parts]), whole.rows())
+    assert np.array_equal(np.concatenate([p.piece for p in parts]), whole.piece)
+    s = sum(p.stats.cpu().numpy() for p in parts)
+    s[10:12] = np.max([p.stats.cpu().numpy()[10:12] for p in parts], axis=0)
+    assert np.array_equal(s, whole.stats.cpu().numpy())
+
+
+def test_step_errors_and_slots():
+    from tetris_b200 import BatchedTetris
+    env = BatchedTetris(10, 20, 64, piece_set=1, seed=1)
+    with pytest.raises(IndexError):
+        env.step(np.full(64, 40, np.int32))            # game.py:83 IndexError
+    with pytest.raises(IndexError):
+        env.step(np.full(64, -1, np.int32))
+    before = env.rows().copy()
+    assert not before.any()                             # failed steps leave the envs untouched
+    # slot-indexed actions == rank-indexed actions while every slot is legal
+    a = np.arange(64, dtype=np.int32) % 9
+    env2 = BatchedTetris(10, 20, 64, piece_set=1, seed=1)
+    o1 = env.step(a)
+    o2 = env2.step(a, action_is_slot=True)
+    for x, y in zip(o1, o2):
+        assert np.array_equal(x.cpu().numpy(), y.cpu().numpy())
+    assert np.array_equal(env.rows(), env2.rows())
+
+
+def test_million_envs_properties():
+    """BASELINE config 3 at full size: 1M envs x every rotation x column placement.  Too many for the oracle,
+    so: (1) bit-exact parity on a strided 4096-env sample, (2) size-independent invariants on all of them."""
+    torch = _torch()
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris, _lib
+    n, seed = 1 << 20, 2024
+    env = BatchedTetris(10, 20, n, piece_set=1, seed=seed)
+    env.rollout(30, "random")                            # realistic boards: ~30 random placements each
+    feats, valid, count = env.get_after_states()
+    rows, heights, piece = env.export_boards()
+    piece_np = piece.cpu().numpy()
+    n_all = torch.as_tensor(np.array([_lib.lib().tb_num_slots(p, 10) for p in range(9)], np.int64), device="cuda")[piece.long()]
+    # invariants on all 1M envs
+    assert bool((count.long() == torch.stack([(valid >> s) & 1 for s in range(env.a_max)]).sum(0)).all())
+    assert bool((count.long() <= n_all).all()) and bool((count > 0).all())
+    slot = torch.arange(env.a_max, device="cuda")[None, :]
+    live = slot < n_all[:, None]
+    f = feats[live]
+    assert bool((f[:, 1] >= 10).all())                   # column_transitions >= C
+    assert bool((f[:, 0] <= f[:, 2]).all())              # rows_with_holes <= holes
+    assert bool(((f * 2) == (f * 2).round()).all())      # half-integers only
+    assert bool((f[:, 6] >= 0).all()) and bool((f[:, 3] >= 1).all())
+    # sample parity
+    sel = np.arange(0, n, n // 4096)[:4096]
+    ob = orc.Batch(10, 20, len(sel), piece_set=1)
+    ob.rep[:] = rows_to_rep(rows.cpu().numpy().view(np.uint16)[sel], 10)
+    ob.heights[:] = heights.cpu().numpy()[sel]
+    ob.piece[:] = piece_np[sel]
+    of, ov, oc, on = ob.afterstates()
+    fs = feats[torch.as_tensor(sel, device="cuda")].cpu().numpy()
+    mask = np.arange(env.a_max)[None, :] < on[:, None]
+    assert np.array_equal(fs[mask], of[mask])
+    assert np.array_equal(valid.cpu().numpy().view(np.uint64)[sel], ov)
+    assert np.array_equal(count.cpu().numpy()[sel], oc)
+
+
+def test_eval_states():
+    """tb_eval_states == State(representation).get_features() (state.py:5-38) on arbitrary boards."""
+    torch = _torch()
+    from oracle import oracle as orc
+    from tetris_b200 import _lib
+    rng = np.random.default_rng(5)
+    for (Cc, R) in SHAPES:
+        N = R + 4
+        reps = (rng.random((200, N, Cc)) < rng.random((200, 1, 1))).astype(np.uint8)
+        reps[:, R:, :] = 0
+        reps[:50, 0, :] = 1                               # full bottom row: cleared by State.__init__ (changed_lines=[0])
+        rows = torch.as_tensor(rep_to_rows(reps).view(np.int16), device="cuda")
+        rows_o = torch.empty_like(rows)
+        h_o = torch.empty((200, Cc), dtype=torch.uint8, device="cuda")
+        info = torch.empty((200, 4), dtype=torch.int32, device="cuda")
+        f = torch.empty((200, 8), dtype=torch.float32, device="cuda")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib().tb_eval_states(Cc, R, 200, p(rows), None, p(rows_o), p(h_o), p(info), p(f), None))
+        torch.cuda.synchronize()
+        for i in range(200):
+            o = orc.board_features(Cc, R, reps[i])
+            assert np.array_equal(f[i].cpu().numpy(), o["features"]), (Cc, R, i)
+            assert np.array_equal(h_o[i].cpu().numpy(), o["heights"])
+            assert np.array_equal(rows_o[i].cpu().numpy().view(np.uint16), rep_to_rows(o["rep"]))
+            assert int(info[i, 0]) == o["n_cleared"] and bool(info[i, 2]) == o["terminal"]

@@ -1,0 +1,179 @@
+"""BatchedTetris: n lockstep envs on one GPU, tensors in / tensors out.
+
+Semantics per env are exactly the reference's Tetris (game.py:8-127): `get_after_states` enumerates the
+current piece's placements in the reference's action order, `step(a)` takes the a-th NON-terminal afterstate
+(game.py:69,83), rewards are lines-1 (-100 more on game over), a finished env is reset by the caller
+(`reset_masked`) or in place (`auto_reset=True`, what example_play.py:20-21 does).
+All compute runs in the CUDA kernels of csrc/tb_kernels.cu; torch only owns memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import BCTS_WEIGHTS, _lib
+
+_PIECE_SET_NAMES = {"default": 0, "threes": 0, 0: 0, "tetrominoes": 1, "seven": 1, 1: 1}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedTetris:
+    def __init__(self, num_columns, num_rows, n_env, piece_set=1, seed=0, env_offset=0, device=None,
+                 feature_directions=None):
+        L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("tetris_b200: no CUDA device; the batched environment has no CPU path")
+        self.num_columns, self.num_rows = int(num_columns), int(num_rows)
+        self.n_env, self.seed, self.env_offset = int(n_env), int(seed) & (2 ** 64 - 1), int(env_offset)
+        self.piece_set = _PIECE_SET_NAMES[piece_set]
+        if not L.tb_supported_shape(self.num_columns, self.num_rows):
+            raise ValueError("board shape %dx%d is not compiled in (see TB_SHAPES in csrc/tb_kernels.cu)"
+                             % (self.num_columns, self.num_rows))
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.a_max = L.tb_a_max(self.num_columns, self.piece_set)
+        self.n_stored_rows = self.num_rows + 4
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros(L.tb_state_bytes(self.num_columns, self.num_rows, self.n_env),
+                                     dtype=torch.uint8, device=self.device)
+            self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.stats = torch.zeros(len(_lib.STATS), dtype=torch.int64, device=self.device)
+        self.set_directions(feature_directions)
+        self.reset()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _common(self):
+        return (_ptr(self.state), self.num_columns, self.num_rows, self.n_env)
+
+    def _dev_u8(self, x):
+        if x is None:
+            return None
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=torch.uint8).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(x, dtype=np.uint8), device=self.device)
+
+    def set_directions(self, feature_directions):
+        """feature_directions (state.py:49-50): per-feature multipliers applied to get_after_states / step obs."""
+        if feature_directions is None:
+            self._dirs = None
+        else:
+            d = np.ascontiguousarray(feature_directions, dtype=np.float32)
+            assert d.shape == (8,)
+            self._dirs = d
+
+    # -- reference surface, batched ---------------------------------------------------------
+    def reset(self, tape=None):
+        """Tetris.__init__ + reset for every env (game.py:21-63).  tape: uint8[n_env] first pieces (global ids)."""
+        t = self._dev_u8(tape)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
+                                           _ptr(t), None, self._stream()))
+
+    def reset_masked(self, mask, tape=None):
+        """Tetris.reset() (game.py:53-63) on the envs where mask is set: board emptied, one more piece drawn."""
+        m, t = self._dev_u8(mask), self._dev_u8(tape)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
+                                           _ptr(t), _ptr(m), self._stream()))
+
+    def get_after_states(self, out=None):
+        """Tetris.get_after_states(include_terminal=True) for every env (game.py:67-80).
+
+        Returns (features float32[n_env, a_max, 8] by enumeration slot, valid int64[n_env] bit mask of
+        non-terminal slots, count int32[n_env]).  Legal action k of env e is the k-th set bit of valid[e].
+        """
+        if out is None:
+            feats = torch.empty((self.n_env, self.a_max, 8), dtype=torch.float32, device=self.device)
+            valid = torch.empty(self.n_env, dtype=torch.int64, device=self.device)
+            count = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
+        else:
+            feats, valid, count = out
+        d = None if self._dirs is None else self._dirs.ctypes.data_as(C.c_void_p)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_afterstates(*self._common(), _ptr(feats), _ptr(valid), _ptr(count),
+                                                 self.a_max, d, self._stream()))
+        return feats, valid, count
+
+    def step(self, actions, tape=None, auto_reset=False, action_is_slot=False, check=True):
+        """Tetris.step for every env (game.py:82-92).  Returns (obs f32[n,8], reward i32[n], done bool[n], lines i32[n])."""
+        if isinstance(actions, torch.Tensor):
+            a = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        else:
+            a = torch.as_tensor(np.ascontiguousarray(actions, dtype=np.int32), device=self.device)
+        if a.shape != (self.n_env,):
+            raise ValueError("actions must have shape (n_env,)")
+        t = self._dev_u8(tape)
+        obs = torch.empty((self.n_env, 8), dtype=torch.float32, device=self.device)
+        reward = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
+        done = torch.empty(self.n_env, dtype=torch.uint8, device=self.device)
+        lines = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
+        flags = (_lib.FLAG_AUTO_RESET if auto_reset else 0) | (_lib.FLAG_ACTION_IS_SLOT if action_is_slot else 0)
+        with torch.cuda.device(self.device):
+            if check:
+                self._status.zero_()
+            _lib.check(_lib.lib().tb_step(*self._common(), self.env_offset, self.seed, self.piece_set, _ptr(a), _ptr(t),
+                                          _ptr(obs), _ptr(reward), _ptr(done), _ptr(lines),
+                                          _ptr(self._status) if check else None, flags, self._stream()))
+            if check and int(self._status.item()) != 0:
+                raise IndexError("action out of range for at least one env (game.py:83)")
+        if self._dirs is not None:
+            obs = obs * torch.as_tensor(self._dirs, device=self.device)
+        return obs, reward, done.bool(), lines
+
+    def rollout(self, n_steps, policy="greedy", weights=None):
+        """n_steps placements per env with an in-kernel policy and auto-reset; adds into self.stats (device)."""
+        pol = {"random": _lib.POLICY_RANDOM, "greedy": _lib.POLICY_GREEDY, 0: 0, 1: 1}[policy]
+        w = np.ascontiguousarray(BCTS_WEIGHTS if weights is None else weights, dtype=np.float32)
+        assert w.shape == (8,)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_rollout(*self._common(), self.env_offset, self.seed, self.piece_set, int(n_steps),
+                                             pol, w.ctypes.data_as(C.c_void_p), _ptr(self.stats), self._stream()))
+        return self.stats
+
+    def stats_dict(self, stats=None):
+        s = (self.stats if stats is None else stats).cpu().tolist()
+        return dict(zip(_lib.STATS, s))
+
+    # -- state interchange --------------------------------------------------------------------
+    def export_boards(self, first=0, count=None):
+        """(rows uint16->int16 tensor [count, R+4] of row masks, heights uint8 [count, C], piece uint8 [count])."""
+        count = self.n_env - first if count is None else count
+        rows = torch.empty((count, self.n_stored_rows), dtype=torch.int16, device=self.device)
+        heights = torch.empty((count, self.num_columns), dtype=torch.uint8, device=self.device)
+        piece = torch.empty(count, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_export_boards(*self._common(), first, count, _ptr(rows), _ptr(heights), _ptr(piece),
+                                                   self._stream()))
+        return rows, heights, piece
+
+    def import_boards(self, rows, piece=None, first=0):
+        """Upload boards as row masks (uint16 per row, bit c = column c); heights are recomputed on the device."""
+        r = np.ascontiguousarray(rows.cpu().numpy() if isinstance(rows, torch.Tensor) else rows).astype(np.uint16)
+        r = torch.as_tensor(r.view(np.int16), device=self.device)
+        if r.dim() != 2 or r.shape[1] != self.n_stored_rows:
+            raise ValueError("rows must have shape (count, num_rows + 4)")
+        p = self._dev_u8(piece)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_import_boards(*self._common(), first, r.shape[0], _ptr(r), _ptr(p), self._stream()))
+
+    # numpy conveniences (host copies)
+    def rows(self):
+        return self.export_boards()[0].cpu().numpy().view(np.uint16)
+
+    @property
+    def heights(self):
+        return self.export_boards()[1].cpu().numpy()
+
+    @property
+    def piece(self):
+        return self.export_boards()[2].cpu().numpy()
+
+    def representation(self, env=0):
+        """(num_rows+4, num_columns) int64 0/1 array of one env, the reference's State.representation."""
+        rows = self.export_boards(env, 1)[0].cpu().numpy().view(np.uint16)[0]
+        return ((rows[:, None] >> np.arange(self.num_columns, dtype=np.uint16)) & 1).astype(np.int64)

@@ -376,13 +376,20 @@ struct Eval {
     int terminal;        // State.terminal_state
 };
 
-// hard-drop row of orientation `d` at column c given column heights h[0..C)
-TB_HD int anchor_row(uint32_t d, const int *h, int c)
+// hard-drop row of orientation `d` anchored at column c (tetromino.py: anchor_row = max(h - bottom)).
+// Static indexing over the board's columns so `col` can stay in registers.
+template <int C>
+TB_HD int anchor_from_cols(const uint32_t *col, uint32_t d, int c)
 {
     int a = 0;
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx)
-        if (desc_len(d, dx) > 0) a = imax(a, h[c + dx] - desc_bot(d, dx));
+    for (int k = 0; k < C; ++k) {
+        const unsigned dx = (unsigned)(k - c);
+        if (dx < 4u) {
+            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+            if (f >> 2) a = imax(a, height_of(col[k]) - (int)(f & 3u));
+        }
+    }
     return a;
 }
 
@@ -392,26 +399,30 @@ template <int C, int R>
 TB_HD int place_and_clear(uint32_t *col, uint32_t d, int c, int &a_out, uint32_t &full_out, int &terminal)
 {
     using S = Shape<C, R>;
-    int a = 0;
-#pragma unroll
-    for (int dx = 0; dx < 4; ++dx)
-        if (desc_len(d, dx) > 0) a = imax(a, height_of(col[imin(c + dx, C - 1)]) - desc_bot(d, dx));
-    uint32_t pm[4];
-#pragma unroll
-    for (int dx = 0; dx < 4; ++dx) pm[dx] = mask_lo(desc_len(d, dx)) << (a + desc_bot(d, dx));
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-        const int dx = k - c;
-        if (dx >= 0 && dx < 4) col[k] |= pm[dx];
-    }
+    const int a = anchor_from_cols<C>(col, d, c);
     uint32_t full = S::ALL;
 #pragma unroll
-    for (int k = 0; k < C; ++k) full &= col[k];
+    for (int k = 0; k < C; ++k) {
+        const unsigned dx = (unsigned)(k - c);
+        if (dx < 4u) {
+            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+            col[k] |= mask_lo((int)(f >> 2)) << (a + (int)(f & 3u));
+        }
+        full &= col[k];
+    }
     full &= mask_lo(desc_chg(d)) << a;                           // only changed_lines are tested (state.py:122)
     int cells = 0;
+    if (full) {
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx) cells += popc32(pm[dx] & full);
-    if (full) clear_rows<C>(col, full);
+        for (int k = 0; k < C; ++k) {
+            const unsigned dx = (unsigned)(k - c);
+            if (dx < 4u) {
+                const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+                cells += popc32((mask_lo((int)(f >> 2)) << (a + (int)(f & 3u))) & full);
+            }
+        }
+        clear_rows<C>(col, full);
+    }
     uint32_t any = 0;
 #pragma unroll
     for (int k = 0; k < C; ++k) any |= col[k];
@@ -622,10 +633,11 @@ TB_HD float fitness(const float *f, const float *w)
 
 // Is the placement a legal action, i.e. a non-terminal afterstate (game.py:69)?  Cheap in the common
 // case (heights only); falls back to an exact place-and-clear when the piece reaches row R.
+// Precondition: the current board has no cell in rows >= R.
 template <int C, int R>
-TB_HD bool placement_valid(const uint32_t *col, const int *h, uint32_t d, int c)
+TB_HD bool placement_valid(const uint32_t *col, uint32_t d, int c)
 {
-    const int a = anchor_row(d, h, c);
+    const int a = anchor_from_cols<C>(col, d, c);
     if (a + desc_ph(d) <= R) return true;
     uint32_t nc[C];
 #pragma unroll
@@ -633,6 +645,34 @@ TB_HD bool placement_valid(const uint32_t *col, const int *h, uint32_t d, int c)
     int aa, term; uint32_t full;
     place_and_clear<C, R>(nc, d, c, aa, full, term);
     return term == 0;
+}
+
+// State.__init__ on a caller-supplied board (state.py:5-38): clear the full rows among the `chg` changed lines
+// starting at row a, terminal test, features.  ppcr = pieces_per_changed_row packed 4 bits each.
+template <int C, int R>
+TB_HD void eval_state(uint32_t *col, int a, int chg, uint32_t ppcr, int bonus2, Eval &e)
+{
+    using S = Shape<C, R>;
+    uint32_t full = S::ALL;
+#pragma unroll
+    for (int k = 0; k < C; ++k) full &= col[k];
+    full &= mask_lo(chg) << a;
+    int eroded = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < chg && ((full >> (a + k)) & 1u)) eroded += (int)((ppcr >> (4 * k)) & 15u);
+    if (full) clear_rows<C>(col, full);
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) any |= col[k];
+    int six[6];
+    eval_full<C, R>(col, six);
+    e.a = a; e.full = full; e.terminal = (int)((any >> R) & 1u);
+    e.f[0] = (float)six[0]; e.f[1] = (float)six[1]; e.f[2] = (float)six[2];
+    e.f[3] = (float)(2 * (a + 1) + bonus2) * 0.5f;
+    e.f[4] = (float)six[3]; e.f[5] = (float)six[4];
+    e.f[6] = (float)(eroded * popc32(full));
+    e.f[7] = (float)six[5];
 }
 
 }  // namespace tb
