@@ -50,6 +50,8 @@ extern "C" {
 /* tb_step / tb_afterstates flags */
 #define TB_FLAG_AUTO_RESET     1   /* step: reset a finished env in place (what example_play.py:20-21 does) */
 #define TB_FLAG_ACTION_IS_SLOT 2   /* step: actions index enumeration slots instead of non-terminal ranks   */
+#define TB_FLAG_INCLUDE_TERMINAL 4 /* afterstates: also write the feature rows of terminal afterstates
+                                      (get_after_states(include_terminal=True), game.py:74-78)               */
 
 /* tb_rollout policies */
 #define TB_POLICY_RANDOM 0         /* uniformly random legal placement (per-env counter RNG, stream 1)       */
@@ -88,16 +90,20 @@ int tb_reset(void *state, int num_columns, int num_rows, int64_t n_env, int64_t 
              int piece_set, const uint8_t *piece_tape, const uint8_t *reset_mask, void *stream);
 
 /*
- * Tetris.get_after_states(include_terminal=True) (game.py:67-80) for every env: enumerate every
- * rotation x column placement of the current piece (tetromino.py:*.get_after_states), drop, lock, clear
- * (state.py:121-143), terminal test (state.py:111-117) and the eight BCTS features (state.py:97-107,175-280).
- *   feats_out   float32[n_env][a_stride][8], by enumeration slot (rows >= tb_num_slots(piece) are not written)
- *   valid_out   uint64[n_env]: bit s set  <=>  slot s is a non-terminal afterstate (a legal action)
- *   count_out   int32[n_env]: number of legal actions (len(self.afterstates), game.py:69)
+ * Tetris.get_after_states (game.py:67-80) for every env: enumerate every rotation x column placement of the
+ * current piece (tetromino.py:*.get_after_states), drop, lock, clear (state.py:121-143), terminal test
+ * (state.py:111-117) and the eight BCTS features (state.py:97-107,175-280).
+ *   feats_out   float32[n_env][a_stride][8], by enumeration slot.  Rows of non-terminal afterstates (the ones
+ *               game.py:69 keeps) are always written; rows of terminal afterstates only with
+ *               TB_FLAG_INCLUDE_TERMINAL (game.py:74-78); rows >= tb_num_slots(piece) never.
+ *   valid_out   nullable uint64[n_env]: bit s set  <=>  slot s is a non-terminal afterstate (a legal action)
+ *   count_out   nullable int32[n_env]: number of legal actions (len(self.afterstates), game.py:69)
  *   directions  nullable HOST float[8]: per-feature multipliers (feature_directions, state.py:49-50), applied in fp32
+ *   flags       0 or TB_FLAG_INCLUDE_TERMINAL
  */
 int tb_afterstates(const void *state, int num_columns, int num_rows, int64_t n_env, float *feats_out,
-                   uint64_t *valid_out, int32_t *count_out, int a_stride, const float *directions, void *stream);
+                   uint64_t *valid_out, int32_t *count_out, int a_stride, const float *directions, int flags,
+                   void *stream);
 
 /*
  * Afterstates with their boards, for the single-env State objects of the compatibility layer

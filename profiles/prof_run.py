@@ -1,0 +1,28 @@
+"""Small fixed workload for ncu: every kernel of the hot path, twice (first launch = warm-up).
+
+    python profiles/prof_run.py [n_env] [rollout_steps]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from tetris_b200 import BatchedTetris
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+env = BatchedTetris(10, 20, n, piece_set=1, seed=0x5EED)
+env.rollout(30, "random")
+for _ in range(2):
+    env.rollout(T, "greedy")
+for _ in range(2):
+    env.rollout(T, "random")
+feats = valid = count = None
+for _ in range(2):
+    feats, valid, count = env.get_after_states()
+for _ in range(2):
+    env.step(torch.zeros(n, dtype=torch.int32, device="cuda"), auto_reset=True, check=False)
+torch.cuda.synchronize()
+print("ok", env.stats_dict())

@@ -12,6 +12,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
                          int32_t *ncleared, uint16_t *rows_out, int32_t *anchor, uint8_t *used_fast)
 {
     using S = Shape<C, R>;
+    uint8_t term_fast[64] = {0};
     uint32_t w[S::NW];
     std::memset(w, 0, sizeof w);
     for (int r = 0; r < S::N; ++r) w[r >> 1] |= (uint32_t)rows[r] << (16 * (r & 1));
@@ -28,7 +29,12 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
         const uint32_t d = kOriHost[ori];
         Eval e;
         uint32_t nc[C];
-        bool fast = (mode == 0) && eval_fast<C, R>(rec, d, c, e);
+        static uint16_t runtab[RunTab<R>::SIZE];
+        static bool init = false;
+        if (!init) { for (int m = 0; m < RunTab<R>::SIZE; ++m) runtab[m] = run_tab_entry<R>((uint32_t)m); init = true; }
+        const int status = (mode == 0) ? eval_fast<C, R>(rec, runtab, d, c, e) : kFastClears;
+        bool fast = status == kFastDone;
+        if (status == kFastTerminal) term_fast[s] = 1;
         if (!fast) eval_slow<C, R>(col, d, c, e, nc);
         else {
             // afterstate board of a fast-path placement: place without clearing
@@ -44,6 +50,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
         for (int r = 0; r < S::N; ++r) rows_out[s * S::N + r] = (uint16_t)(wo[r >> 1] >> (16 * (r & 1)));
         // placement_valid must agree with the terminal flag
         if (placement_valid<C, R>(col, d, c) != (e.terminal == 0)) return -1;
+        if (term_fast[s] && !(e.terminal && e.full == 0u)) return -3;     // kFastTerminal must mean terminal, no clear
     }
     return n;
 }

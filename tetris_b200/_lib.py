@@ -17,6 +17,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 NUM_FEATURES = 8
 FLAG_AUTO_RESET = 1
 FLAG_ACTION_IS_SLOT = 2
+FLAG_INCLUDE_TERMINAL = 4
 POLICY_RANDOM = 0
 POLICY_GREEDY = 1
 STATS = ("placements", "episodes", "lines", "reward", "afterstates",
@@ -69,7 +70,7 @@ def lib():
     L.tb_reset.restype = i32
     L.tb_reset.argtypes = [vp, i32, i32, i64, i64, u64, i32, vp, vp, vp]
     L.tb_afterstates.restype = i32
-    L.tb_afterstates.argtypes = [vp, i32, i32, i64, vp, vp, vp, i32, vp, vp]
+    L.tb_afterstates.argtypes = [vp, i32, i32, i64, vp, vp, vp, i32, vp, i32, vp]
     L.tb_afterstates_export.restype = i32
     L.tb_afterstates_export.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, i32, vp]
     L.tb_step.restype = i32

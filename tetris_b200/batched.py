@@ -81,11 +81,13 @@ class BatchedTetris:
             _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
                                            _ptr(t), _ptr(m), self._stream()))
 
-    def get_after_states(self, out=None):
-        """Tetris.get_after_states(include_terminal=True) for every env (game.py:67-80).
+    def get_after_states(self, include_terminal=False, out=None):
+        """Tetris.get_after_states for every env (game.py:67-80).
 
         Returns (features float32[n_env, a_max, 8] by enumeration slot, valid int64[n_env] bit mask of
         non-terminal slots, count int32[n_env]).  Legal action k of env e is the k-th set bit of valid[e].
+        Feature rows of terminal afterstates are written only with include_terminal=True (game.py:74-78);
+        rows past the piece's slot count are never written.
         """
         if out is None:
             feats = torch.empty((self.n_env, self.a_max, 8), dtype=torch.float32, device=self.device)
@@ -96,7 +98,9 @@ class BatchedTetris:
         d = None if self._dirs is None else self._dirs.ctypes.data_as(C.c_void_p)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().tb_afterstates(*self._common(), _ptr(feats), _ptr(valid), _ptr(count),
-                                                 self.a_max, d, self._stream()))
+                                                 self.a_max, d,
+                                                 _lib.FLAG_INCLUDE_TERMINAL if include_terminal else 0,
+                                                 self._stream()))
         return feats, valid, count
 
     def step(self, actions, tape=None, auto_reset=False, action_is_slot=False, check=True):

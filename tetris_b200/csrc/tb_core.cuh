@@ -537,12 +537,57 @@ TB_HD void build_env(const uint32_t *col, uint32_t *rec)
     rec[K::T_HMAX] = (uint32_t)hmax;
 }
 
+// ---------------------------------------------------------------------------------------------
+// run-sum by table.  A well mask of a non-terminal board has bits only below row R, so it splits into two halves
+// of HB = ceil(R / 2) bits; the table has 2^HB uint16 entries, entry for a half m = run_sum(m) | trail << 7 |
+// lead << 11 where trail / lead = length of the run of ones touching the half's bit 0 / bit HB-1.  A column is two
+// lookups plus the cross term of a run spanning the halves: (p+q)(p+q+1)/2 = p(p+1)/2 + q(q+1)/2 + p*q.
+// No POPC, no data-dependent loop.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+struct RunTab {
+    static constexpr int HB = (R + 1) / 2;
+    static constexpr int SIZE = 1 << HB;
+    static_assert(HB <= 12, "run table entries hold runs of at most 15 cells");
+};
+template <int R>
+TB_HD uint16_t run_tab_entry(uint32_t m)
+{
+    constexpr int HB = RunTab<R>::HB;
+    const int rs = run_sum(m);
+    int trail = 0, lead = 0;
+    while (trail < HB && ((m >> trail) & 1u)) ++trail;
+    while (lead < HB && ((m >> (HB - 1 - lead)) & 1u)) ++lead;
+    return (uint16_t)(rs | (trail << 7) | (lead << 11));
+}
+template <int R>
+TB_HD int run_sum_tab(const uint16_t *tab, uint32_t w)   // w < 2^R
+{
+    constexpr int HB = RunTab<R>::HB;
+    const uint32_t e0 = tab[w & (uint32_t)(RunTab<R>::SIZE - 1)], e1 = tab[w >> HB];
+    return (int)((e0 & 127u) + (e1 & 127u) + (e0 >> 11) * ((e1 >> 7) & 15u));
+}
+
+// small non-negative int -> float without the (quarter-rate) I2F conversion unit
+TB_HD float u2f(int v)
+{
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(0x4B000000 | v) - 8388608.0f;
+#else
+    return (float)v;
+#endif
+}
+
+// eval_fast status
+constexpr int kFastDone = 0;      // features written, afterstate is legal
+constexpr int kFastClears = 1;    // a line clears: needs the general path
+constexpr int kFastTerminal = 2;  // no line clears and the piece reaches row R: terminal afterstate
+
 // Fast path: placement that clears no line and stays below the top.  Only the piece's columns and
-// their neighbours are re-evaluated; everything else comes from the env record.  Returns false when
-// the placement needs the general path (a line clears, or the piece reaches row R).
+// their neighbours are re-evaluated; everything else comes from the env record.  Branch-free.
 // Precondition: every column height of the current board is <= R (a non-terminal state).
 template <int C, int R>
-TB_HD bool eval_fast(const uint32_t *rec, uint32_t d, int c, Eval &e)
+TB_HD int eval_fast(const uint32_t *rec, const uint16_t *runtab, uint32_t d, int c, Eval &e)
 {
     using S = Shape<C, R>;
     using K = Rec<C, R>;
@@ -557,9 +602,10 @@ TB_HD bool eval_fast(const uint32_t *rec, uint32_t d, int c, Eval &e)
     for (int k = 0; k < 6; ++k) nh[k] = (int)((hw >> (5 * k)) & 31u);
     int a = 0;
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx)
-        if (desc_len(d, dx) > 0) a = imax(a, nh[1 + dx] - desc_bot(d, dx));
-
+    for (int dx = 0; dx < 4; ++dx) {
+        const int len = desc_len(d, dx);
+        a = imax(a, len > 0 ? nh[1 + dx] - desc_bot(d, dx) : 0);
+    }
     uint32_t y[8];                                                 // columns c-2 .. c+5 after the placement
 #pragma unroll
     for (int k = 0; k < 8; ++k) y[k] = rec[K::COLX + c + k];
@@ -568,21 +614,22 @@ TB_HD bool eval_fast(const uint32_t *rec, uint32_t d, int c, Eval &e)
 #pragma unroll
     for (int dx = 0; dx < 4; ++dx) {
         const int len = desc_len(d, dx);
-        if (len > 0) {
-            const int lo = a + desc_bot(d, dx);
-            const int g = lo - nh[1 + dx];                         // new holes under the piece in this column
-            y[2 + dx] |= mask_lo(len) << lo;
-            fp &= y[2 + dx];
-            gapsum += g;
-            gapcnt += (g > 0);
-            gapor |= mask_lo(lo) ^ mask_lo(nh[1 + dx]);
-            hdadd += len * ((int)((nrw >> (4 * dx)) & 15u) + (g > 0));
-            nh[1 + dx] = lo + len;
-            lastlen = len;
-        }
+        const bool on = len > 0;
+        const int lo = a + desc_bot(d, dx);
+        const int h = nh[1 + dx];
+        const int g = on ? lo - h : 0;                             // new holes under the piece in this column
+        y[2 + dx] |= mask_lo(len) << lo;                           // len == 0 adds nothing
+        fp &= on ? y[2 + dx] : S::ALL;
+        gapsum += g;
+        gapcnt += (g > 0);
+        gapor |= on ? (mask_lo(lo) ^ mask_lo(h)) : 0u;
+        hdadd += len * ((int)((nrw >> (4 * dx)) & 15u) + (g > 0));
+        nh[1 + dx] = on ? lo + len : h;
+        lastlen = on ? len : lastlen;
     }
     const uint32_t full = rec[K::PAND + c] & rec[K::SAND + c + w] & fp & (mask_lo(desc_chg(d)) << a);
-    if (full != 0u || a + desc_ph(d) > R) return false;
+    if (full != 0u) return kFastClears;
+    if (a + desc_ph(d) > R) return kFastTerminal;
 
     // wells over columns c-1 .. c+4, row transitions over columns c .. c+4 (clipped to the board)
     const int wlo = imax(c - 1, 0), hi = imin(c + 4, C - 1);
@@ -591,29 +638,30 @@ TB_HD bool eval_fast(const uint32_t *rec, uint32_t d, int c, Eval &e)
 #pragma unroll
     for (int k = 1; k <= 6; ++k) {
         const int j = c - 2 + k;
-        if (j >= 0 && j < C) wells += run_sum(y[k - 1] & y[k + 1] & ~y[k]);
+        const uint32_t wm = (j >= 0 && j < C) ? (y[k - 1] & y[k + 1] & ~y[k]) : 0u;
+        wells += run_sum_tab<R>(runtab, wm);
     }
 #pragma unroll
     for (int k = 2; k <= 6; ++k) {
         const int j = c - 2 + k;
-        if (j < C) {
-            const int hj = nh[k - 1], hl = nh[k - 2];
-            if (hj > 0) rt += imax(0, hl - hj) + popc32((y[k] ^ y[k - 1]) & mask_lo(hj));
-            else rt += popc32(y[k - 1]);                           // left neighbour is a real column here
-        }
+        const int hj = nh[k - 1], hl = nh[k - 2];
+        // hj > 0: step down from the left column + cells differing from it; hj == 0: the left column's cells
+        const uint32_t m = hj > 0 ? ((y[k] ^ y[k - 1]) & mask_lo(hj)) : y[k - 1];
+        const int v = popc32(m) + (hj > 0 ? imax(0, hl - hj) : 0);
+        rt += (j < C) ? v : 0;
     }
-    if (c + w == C) rt -= lastlen;                                 // right-wall term R - popc(col[C-1])
+    rt -= (c + w == C) ? lastlen : 0;                              // right-wall term R - popc(col[C-1])
 
     e.a = a; e.full = 0u; e.terminal = 0;
-    e.f[0] = (float)popc32(rec[K::T_HM] | gapor);
-    e.f[1] = (float)((int)rec[K::T_CT] + 2 * gapcnt);
-    e.f[2] = (float)((int)rec[K::T_HOLES] + gapsum);
-    e.f[3] = (float)(2 * (a + 1) + desc_bonus2(d)) * 0.5f;
-    e.f[4] = (float)wells;
-    e.f[5] = (float)rt;
+    e.f[0] = u2f(popc32(rec[K::T_HM] | gapor));
+    e.f[1] = u2f((int)rec[K::T_CT] + 2 * gapcnt);
+    e.f[2] = u2f((int)rec[K::T_HOLES] + gapsum);
+    e.f[3] = u2f(2 * (a + 1) + desc_bonus2(d)) * 0.5f;
+    e.f[4] = u2f(wells);
+    e.f[5] = u2f(rt);
     e.f[6] = 0.0f;
-    e.f[7] = (float)((int)rec[K::T_HD] + hdadd);
-    return true;
+    e.f[7] = u2f((int)rec[K::T_HD] + hdadd);
+    return kFastDone;
 }
 
 // Tetris.fitness (game.py:109-120): float32 products and sums, left to right, no FMA contraction.

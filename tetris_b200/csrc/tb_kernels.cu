@@ -183,11 +183,21 @@ template <int C, int R>
 struct TileSmem {
     using K = Rec<C, R>;
     uint32_t rec[32 * K::WORDS];
-    unsigned long long acc[32];      // K1: legal-slot mask per env; K3: best (score, slot) key per env
+    unsigned long long acc[32];      // K1: legal-slot bits set by the slow path; K3: best (score, slot) key per env
     uint16_t pref[34];
     uint16_t queue[64];
     uint8_t pid[32];
 };
+
+// piece/orientation tables and the run-sum table into shared memory (one barrier)
+template <int R>
+__device__ __forceinline__ void stage_all(uint32_t *s_ori, uint32_t *s_piece, uint16_t *s_run)
+{
+    if (threadIdx.x < kNumOris) s_ori[threadIdx.x] = c_ori[threadIdx.x];
+    if (threadIdx.x < kNumPieces) s_piece[threadIdx.x] = c_piece[threadIdx.x];
+    for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) s_run[m] = run_tab_entry<R>((uint32_t)m);
+    __syncthreads();
+}
 
 __device__ __forceinline__ void emit_features(float *__restrict__ feats, int64_t env, int a_stride, int slot,
                                               const Eval &ev, const F8 &dirs)
@@ -197,31 +207,38 @@ __device__ __forceinline__ void emit_features(float *__restrict__ feats, int64_t
     dst[1] = make_float4(ev.f[4] * dirs.v[4], ev.f[5] * dirs.v[5], ev.f[6] * dirs.v[6], ev.f[7] * dirs.v[7]);
 }
 
-// map flattened item index -> (env in tile, slot)
-__device__ __forceinline__ void find_item(const uint16_t *pref, int i, int &env, int &slot)
+// Flattened item list of a tile: item i belongs to the env whose slot range [pref[env], pref[env+1]) holds i.
+// `heads` has bit j set when item base+j is the first item of an env; `cum` = envs that start before `base`.
+__device__ __forceinline__ uint32_t window_heads(int own_lo, int own_n, int base)
 {
-    int lo = 0, hi = 32;
-#pragma unroll
-    for (int it = 0; it < 5; ++it) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)pref[mid] <= i) lo = mid; else hi = mid;
-    }
-    env = lo;
-    slot = i - (int)pref[lo];
+    const unsigned rel = (unsigned)(own_lo - base);
+    return __reduce_or_sync(FULLMASK, (own_n > 0 && rel < 32u) ? (1u << rel) : 0u);
+}
+// bits of a per-item ballot that fall into the owner lane's slot range, moved to slot positions
+__device__ __forceinline__ unsigned long long window_bits(uint32_t bal, int own_lo, int own_hi, int base)
+{
+    const int s = imax(own_lo, base), t = imin(own_hi, base + 32);
+    if (s >= t) return 0ull;
+    const uint32_t bits = (bal >> (s - base)) & (0xFFFFFFFFu >> (32 - (t - s)));
+    return (unsigned long long)bits << (s - own_lo);
 }
 
 template <int C, int R, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
-              int *__restrict__ count_out, int a_stride, F8 dirs)
+              int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
 {
     using K = Rec<C, R>;
     __shared__ TileSmem<C, R> s_tile[WARPS];
     __shared__ uint32_t s_ori[32], s_piece[16];
-    stage_tables(s_ori, s_piece);
+    __shared__ uint16_t s_run[RunTab<R>::SIZE];
+    stage_all<R>(s_ori, s_piece, s_run);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lane_le = (2u << lane) - 1u;
     TileSmem<C, R> &sm = s_tile[warp];
+    uint32_t *acc32 = reinterpret_cast<uint32_t *>(sm.acc);
     const int64_t n_tiles = (sv.n_env + 31) >> 5;
+    const bool want_terminal = (flags & TB_FLAG_INCLUDE_TERMINAL) != 0;
 
     for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * WARPS) {
         const int64_t e0 = tile * 32, e = e0 + lane;
@@ -242,8 +259,8 @@ k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__res
             const int v = __shfl_up_sync(FULLMASK, incl, o);
             if (lane >= o) incl += v;
         }
-        if (lane == 0) sm.pref[0] = 0;
-        sm.pref[lane + 1] = (uint16_t)incl;
+        const int own_lo = incl - n_slots, own_hi = incl;
+        sm.pref[lane] = (uint16_t)own_lo;
         const int total = __shfl_sync(FULLMASK, incl, 31);
         __syncwarp();
 
@@ -254,46 +271,54 @@ k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__res
             slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
             Eval ev;
             eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, s_ori[ori], c, ev, nullptr);
-            emit_features(feats, e0 + env, a_stride, slot, ev, dirs);
-            if (!ev.terminal) atomicOr(&sm.acc[env], 1ull << slot);
+            if (!ev.terminal || want_terminal) emit_features(feats, e0 + env, a_stride, slot, ev, dirs);
+            if (!ev.terminal) atomicOr(&acc32[2 * env + (slot >> 5)], 1u << (slot & 31));
         };
-        int qn = 0;                                        // warp-uniform queue length
+        unsigned long long vmask = 0ull;                   // owner lane: legal-slot mask of its env
+        int qn = 0, cum = 0;                               // warp-uniform: queue length, envs started before base
         for (int base = 0; base < total; base += 32) {
+            const uint32_t heads = window_heads(own_lo, n_slots, base);
             const int i = base + lane;
-            bool slow = false;
+            bool slow = false, ok = false;
             uint32_t packed = 0;
             if (i < total) {
-                int env, slot, ori, c;
-                find_item(sm.pref, i, env, slot);
+                const int env = cum + __popc(heads & lane_le) - 1;
+                const int slot = i - (int)sm.pref[env];
+                int ori, c;
                 slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
                 Eval ev;
-                if (eval_fast<C, R>(sm.rec + env * K::WORDS, s_ori[ori], c, ev)) {
+                const int status = eval_fast<C, R>(sm.rec + env * K::WORDS, s_run, s_ori[ori], c, ev);
+                if (status == kFastDone) {
                     emit_features(feats, e0 + env, a_stride, slot, ev, dirs);
-                    atomicOr(&sm.acc[env], 1ull << slot);
-                } else {
+                    ok = true;
+                } else if (status == kFastClears || want_terminal) {
                     slow = true;
                     packed = (uint32_t)(env << 8 | slot);
                 }
             }
+            cum += __popc(heads);
+            vmask |= window_bits(__ballot_sync(FULLMASK, ok), own_lo, own_hi, base);
             const unsigned bal = __ballot_sync(FULLMASK, slow);
-            if (slow) sm.queue[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)packed;
-            qn += __popc(bal);
-            __syncwarp();
-            if (qn >= 32) {
-                slow_item(sm.queue[lane]);
+            if (bal) {
+                if (slow) sm.queue[qn + __popc(bal & (lane_le >> 1))] = (uint16_t)packed;
+                qn += __popc(bal);
                 __syncwarp();
-                uint16_t mv = 0;
-                if (lane < qn - 32) mv = sm.queue[32 + lane];
-                __syncwarp();
-                if (lane < qn - 32) sm.queue[lane] = mv;
-                qn -= 32;
-                __syncwarp();
+                if (qn >= 32) {
+                    slow_item(sm.queue[lane]);
+                    __syncwarp();
+                    uint16_t mv = 0;
+                    if (lane < qn - 32) mv = sm.queue[32 + lane];
+                    __syncwarp();
+                    if (lane < qn - 32) sm.queue[lane] = mv;
+                    qn -= 32;
+                    __syncwarp();
+                }
             }
         }
         if (lane < qn) slow_item(sm.queue[lane]);
         __syncwarp();
         if (e < sv.n_env) {
-            const unsigned long long v = sm.acc[lane];
+            const unsigned long long v = vmask | sm.acc[lane];
             if (valid_out) valid_out[e] = v;
             if (count_out) count_out[e] = __popcll(v);
         }
@@ -545,9 +570,11 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
     using K = Rec<C, R>;
     __shared__ TileSmem<C, R> s_tile[WARPS];
     __shared__ uint32_t s_ori[32], s_piece[16];
+    __shared__ uint16_t s_run[RunTab<R>::SIZE];
     __shared__ long long s_blk[TB_ST_COUNT];
-    stage_tables(s_ori, s_piece);
+    stage_all<R>(s_ori, s_piece, s_run);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lane_le = (2u << lane) - 1u;
     TileSmem<C, R> &sm = s_tile[warp];
     const int64_t n_tiles = (sv.n_env + 31) >> 5;
     LaneStats st;
@@ -585,58 +612,85 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 const int v = __shfl_up_sync(FULLMASK, incl, o);
                 if (lane >= o) incl += v;
             }
-            if (lane == 0) sm.pref[0] = 0;
-            sm.pref[lane + 1] = (uint16_t)incl;
+            const int own_lo = incl - n_slots, own_hi = incl;
+            sm.pref[lane] = (uint16_t)own_lo;
             const int total = __shfl_sync(FULLMASK, incl, 31);
             __syncwarp();
-            // ---- phase B: score every legal afterstate, keep the first arg-max per env
-            auto offer = [&](int env, int slot, const Eval &ev) {
-                const float score = fitness(ev.f, wts.v);                       // game.py:109-120
-                const unsigned long long k64 =
-                    ((unsigned long long)orderable(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)slot);
-                atomicMax(&sm.acc[env], k64);
-            };
+            // ---- phase B: score every legal afterstate, keep the first arg-max per env.
+            // Fast-path items: segmented max-scan over the window's lanes (items of an env are contiguous), the env's
+            // owner lane picks up the result of its segment.  Slow-path items (rare): 64-bit atomicMax in shared.
             auto slow_item = [&](uint32_t packed) {
                 const int env = (int)(packed >> 8), slot = (int)(packed & 0xffu);
                 int ori, c;
                 slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
                 Eval ev;
                 eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, s_ori[ori], c, ev, nullptr);
-                if (!ev.terminal) offer(env, slot, ev);
+                if (!ev.terminal) {
+                    const float score = fitness(ev.f, wts.v);                   // game.py:109-120
+                    atomicMax(&sm.acc[env], ((unsigned long long)orderable(score) << 32) |
+                                                (unsigned long long)(0xFFFFFFFFu - (uint32_t)slot));
+                }
             };
-            int qn = 0;
+            uint32_t best_key = 0u;                        // owner lane: best orderable score so far (0 = none)
+            int best_slot = 0;
+            int qn = 0, cum = 0;
             for (int base = 0; base < total; base += 32) {
+                const uint32_t heads = window_heads(own_lo, n_slots, base);
                 const int i = base + lane;
                 bool slow = false;
-                uint32_t packed = 0;
+                uint32_t packed = 0, key = 0u;
+                int slot = 0;
                 if (i < total) {
-                    int env, slot, ori, c;
-                    find_item(sm.pref, i, env, slot);
+                    const int env = cum + __popc(heads & lane_le) - 1;
+                    slot = i - (int)sm.pref[env];
+                    int ori, c;
                     slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
                     Eval ev;
-                    if (eval_fast<C, R>(sm.rec + env * K::WORDS, s_ori[ori], c, ev)) offer(env, slot, ev);
-                    else { slow = true; packed = (uint32_t)(env << 8 | slot); }
+                    const int status = eval_fast<C, R>(sm.rec + env * K::WORDS, s_run, s_ori[ori], c, ev);
+                    if (status == kFastDone) key = orderable(fitness(ev.f, wts.v));
+                    else if (status == kFastClears) { slow = true; packed = (uint32_t)(env << 8 | slot); }
                 }
+                cum += __popc(heads);
+                // lanes below this one that belong to the same env (its segment may have started in an earlier window)
+                const int dist = lane - (31 - __clz((int)(heads & lane_le)));
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t k2 = __shfl_up_sync(FULLMASK, key, o);
+                    const int s2 = __shfl_up_sync(FULLMASK, slot, o);
+                    if (o <= dist && o <= lane && k2 >= key) { key = k2; slot = s2; }   // ties: the earlier slot wins
+                }
+                const int seg_s = imax(own_lo, base), seg_t = imin(own_hi, base + 32);
+                const int src = seg_s < seg_t ? seg_t - 1 - base : lane;
+                const uint32_t k3 = __shfl_sync(FULLMASK, key, src);
+                const int s3 = __shfl_sync(FULLMASK, slot, src);
+                if (seg_s < seg_t && k3 > best_key) { best_key = k3; best_slot = s3; }   // earlier windows win ties
                 const unsigned bal = __ballot_sync(FULLMASK, slow);
-                if (slow) sm.queue[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)packed;
-                qn += __popc(bal);
-                __syncwarp();
-                if (qn >= 32) {
-                    slow_item(sm.queue[lane]);
+                if (bal) {
+                    if (slow) sm.queue[qn + __popc(bal & (lane_le >> 1))] = (uint16_t)packed;
+                    qn += __popc(bal);
                     __syncwarp();
-                    uint16_t mv = 0;
-                    if (lane < qn - 32) mv = sm.queue[32 + lane];
-                    __syncwarp();
-                    if (lane < qn - 32) sm.queue[lane] = mv;
-                    qn -= 32;
-                    __syncwarp();
+                    if (qn >= 32) {
+                        slow_item(sm.queue[lane]);
+                        __syncwarp();
+                        uint16_t mv = 0;
+                        if (lane < qn - 32) mv = sm.queue[32 + lane];
+                        __syncwarp();
+                        if (lane < qn - 32) sm.queue[lane] = mv;
+                        qn -= 32;
+                        __syncwarp();
+                    }
                 }
             }
             if (lane < qn) slow_item(sm.queue[lane]);
             __syncwarp();
             // ---- phase C
             if (active) {
-                const unsigned long long best = sm.acc[lane];
+                unsigned long long best = sm.acc[lane];
+                if (best_key != 0u) {
+                    const unsigned long long k64 = ((unsigned long long)best_key << 32) |
+                                                   (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_slot);
+                    best = k64 > best ? k64 : best;
+                }
                 if (best != 0ull) {
                     const int slot = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
                     int ori, c;
@@ -866,7 +920,7 @@ int tb_reset(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint6
 }
 
 int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_out, uint64_t *valid_out,
-                   int32_t *count_out, int a_stride, const float *directions, void *stream)
+                   int32_t *count_out, int a_stride, const float *directions, int flags, void *stream)
 {
     TB_CHECK_COMMON();
     if (!feats_out) return fail("%s: feats_out is required", __func__);
@@ -877,7 +931,8 @@ int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
         k_afterstates<c, r, WARPS><<<grid_for((n_env + 31) / 32, WARPS, 8), WARPS * 32, 0, st>>>(        \
-            make_view<c, r>(state, n_env), feats_out, (unsigned long long *)valid_out, count_out, a_stride, dirs); \
+            make_view<c, r>(state, n_env), feats_out, (unsigned long long *)valid_out, count_out, a_stride, dirs, \
+            flags);                                                                                      \
         return check_launch("tb_afterstates");                                                           \
     }
     TB_SHAPES(X)
