@@ -172,6 +172,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from tetris_b200 import BCTS_WEIGHTS, BatchedTetris, _lib
+    from tetris_b200.distributed import reduce_stats
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,9 +195,7 @@ def run_ours(args):
     def step():
         env.rollout(T, "greedy", weights)
         if world > 1:
-            red = env.stats.clone()                          # end-of-rollout reduction of episode statistics
-            dist.all_reduce(red, op=dist.ReduceOp.SUM)
-            return red
+            return reduce_stats(env.stats)                   # end-of-rollout reduction of episode statistics (NCCL)
         return env.stats
 
     for _ in range(W):

@@ -75,6 +75,12 @@ int tb_supported_shape(int num_columns, int num_rows);
 size_t tb_state_bytes(int num_columns, int num_rows, int64_t n_env);
 /* Number of afterstates (enumeration slots) of a piece: SURVEY.md Appendix A. */
 int tb_num_slots(int piece, int num_columns);
+/*
+ * The piece x rotation table entry behind enumeration slot `slot` (tetromino.py:33-576).
+ * Host-only.  out int32[17]: [0] anchor_col  [1] width  [2] n_cells  [3] len(changed_lines)
+ *   [4] 2 * landing_height_bonus  [5..8] pieces_per_changed_row  [9..16] the cells as (dx, dy) pairs.
+ */
+int tb_slot_info(int piece, int num_columns, int slot, int32_t *out);
 /* max over the set's pieces = row stride callers should use for per-slot outputs. */
 int tb_a_max(int num_columns, int piece_set);
 
@@ -160,6 +166,12 @@ int tb_import_boards(void *state, int num_columns, int num_rows, int64_t n_env, 
  */
 int tb_eval_states(int num_columns, int num_rows, int64_t n, const uint16_t *rows_in, const int32_t *params,
                    uint16_t *rows_out, uint8_t *heights_out, int32_t *info_out, float *feats_out, void *stream);
+
+/*
+ * Tetris.fitness (game.py:109-120) for n feature rows: float32 products summed left to right, no FMA.
+ *   feats float32[n][8] (device, 16-byte aligned), weights HOST float[8], out float32[n] (device)
+ */
+int tb_fitness(int64_t n, const float *feats, const float *weights, float *out, void *stream);
 
 #ifdef __cplusplus
 }

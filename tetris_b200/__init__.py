@@ -19,4 +19,10 @@ def __getattr__(name):
     if name == "BatchedTetris":
         from .batched import BatchedTetris
         return BatchedTetris
+    if name == "Tetris":
+        from .game import Tetris
+        return Tetris
+    if name in ("game", "state", "tetromino", "utils", "batched", "distributed"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

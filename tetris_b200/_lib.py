@@ -83,13 +83,17 @@ def lib():
     L.tb_import_boards.argtypes = [vp, i32, i32, i64, i64, i64, vp, vp, vp]
     L.tb_eval_states.restype = i32
     L.tb_eval_states.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.tb_slot_info.restype = i32
+    L.tb_slot_info.argtypes = [i32, i32, i32, vp]
+    L.tb_fitness.restype = i32
+    L.tb_fitness.argtypes = [i64, vp, vp, vp, vp]
     _lib = L
     return L
 
 
 EXPORTS = ("tb_version", "tb_last_error", "tb_supported_shape", "tb_state_bytes", "tb_num_slots", "tb_a_max",
            "tb_reset", "tb_afterstates", "tb_afterstates_export", "tb_step", "tb_rollout", "tb_export_boards",
-           "tb_import_boards", "tb_eval_states")
+           "tb_import_boards", "tb_eval_states", "tb_slot_info", "tb_fitness")
 
 
 def check(rc):

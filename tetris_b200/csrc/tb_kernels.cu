@@ -812,6 +812,16 @@ __global__ void k_eval_states(int64_t n, const uint16_t *__restrict__ rows_in, c
     }
 }
 
+// Tetris.fitness (game.py:109-120) of n feature rows
+__global__ void k_fitness(int64_t n, const float *__restrict__ feats, F8 wts, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = reinterpret_cast<const float4 *>(feats)[2 * i], b = reinterpret_cast<const float4 *>(feats)[2 * i + 1];
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    out[i] = fitness(f, wts.v);
+}
+
 }  // namespace tb
 
 // =============================================================================================
@@ -896,6 +906,28 @@ int tb_a_max(int C, int piece_set)
         if (n > m) m = n;
     }
     return m;
+}
+
+int tb_slot_info(int piece, int C, int slot, int32_t *out)
+{
+    if (piece < 0 || piece >= kNumPieces || !out) return fail("%s: bad piece or null output", __func__);
+    const uint32_t pw = kPieceHost[piece];
+    if (C < 4 || slot < 0 || slot >= piece_num_slots(pw, C)) return fail("%s: slot out of range", __func__);
+    int ori, c;
+    slot_to_placement(pw, C, slot, ori, c);
+    const uint32_t d = kOriHost[ori];
+    int n = 0;
+    for (int i = 0; i < 17; ++i) out[i] = 0;
+    out[0] = c; out[1] = desc_w(d); out[3] = desc_chg(d); out[4] = desc_bonus2(d);
+    for (int dx = 0; dx < 4; ++dx)
+        for (int k = 0; k < desc_len(d, dx); ++k) {
+            const int dy = desc_bot(d, dx) + k;
+            out[9 + 2 * n] = dx; out[10 + 2 * n] = dy;
+            if (dy < desc_chg(d)) out[5 + dy] += 1;                 // pieces_per_changed_row
+            ++n;
+        }
+    out[2] = n;
+    return 0;
 }
 
 #define TB_CHECK_COMMON()                                                                   \
@@ -1059,6 +1091,15 @@ int tb_eval_states(int C, int R, int64_t n, const uint16_t *rows_in, const int32
     TB_SHAPES(X)
 #undef X
     return -1;
+}
+
+int tb_fitness(int64_t n, const float *feats, const float *weights, float *out, void *stream)
+{
+    if (n <= 0) return fail("%s: n must be positive", __func__);
+    if (!feats || !weights || !out) return fail("%s: null argument", __func__);
+    if ((reinterpret_cast<uintptr_t>(feats) & 15u) != 0) return fail("%s: feats must be 16-byte aligned", __func__);
+    k_fitness<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, feats, f8_from(weights, 0.0f), out);
+    return check_launch("tb_fitness");
 }
 
 }  // extern "C"
