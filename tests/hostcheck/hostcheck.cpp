@@ -12,45 +12,50 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
                          int32_t *ncleared, uint16_t *rows_out, int32_t *anchor, uint8_t *used_fast)
 {
     using S = Shape<C, R>;
-    uint8_t term_fast[64] = {0};
     uint32_t w[S::NW];
     std::memset(w, 0, sizeof w);
     for (int r = 0; r < S::N; ++r) w[r >> 1] |= (uint32_t)rows[r] << (16 * (r & 1));
     uint32_t col[C];
     rows_to_cols<C, R>(w, col);
-    uint32_t rec[Rec<C, R>::WORDS + 8];
+    static uint16_t runtab[RunTab<R>::SIZE];
+    static bool init = false;
+    if (!init) { for (int m = 0; m < RunTab<R>::SIZE; ++m) runtab[m] = run_tab_entry<R>((uint32_t)m); init = true; }
+    uint32_t rec[Env<C, R>::WORDS + 8];
     std::memset(rec, 0, sizeof rec);
-    build_env<C, R>(col, rec);
+    uint32_t any = 0;
+    for (int k = 0; k < C; ++k) any |= col[k];
+    const int hmax = height_of(any);
+    if (hmax <= R) build_env<C, R>(col, runtab, rec);      // the record's precondition: a non-terminal board
     const uint32_t pw = kPieceHost[piece];
     const int n = piece_num_slots(pw, C);
     for (int s = 0; s < n; ++s) {
         int ori, c;
         slot_to_placement(pw, C, s, ori, c);
         const uint32_t d = kOriHost[ori];
-        Eval e;
+        Eval quick, full;
         uint32_t nc[C];
-        static uint16_t runtab[RunTab<R>::SIZE];
-        static bool init = false;
-        if (!init) { for (int m = 0; m < RunTab<R>::SIZE; ++m) runtab[m] = run_tab_entry<R>((uint32_t)m); init = true; }
-        const int status = (mode == 0) ? eval_fast<C, R>(rec, runtab, d, c, e) : kFastClears;
-        bool fast = status == kFastDone;
-        if (status == kFastTerminal) term_fast[s] = 1;
-        if (!fast) eval_slow<C, R>(col, d, c, e, nc);
-        else {
-            // afterstate board of a fast-path placement: place without clearing
-            Eval e2; eval_slow<C, R>(col, d, c, e2, nc);
+        // mode 0: the incremental path the kernels use, falling back to the general path exactly where they do
+        const int status = (mode == 0 && hmax <= R) ? eval_placement_w<C, R>(rec, runtab, d, c, quick) : -1;
+        eval_slow<C, R>(col, d, c, full, nc);                      // also yields the afterstate board
+        const bool fast = status == kFastDone;
+        if (status >= 0) {
+            // what eval_placement reports on its early exits must agree with the general path
+            if (quick.a != full.a || quick.terminal != full.terminal) return -3;
+            if (status != kFastTerminal && quick.full != full.full) return -4;
+            if (status == kFastTerminal && !(full.terminal && full.full == 0u)) return -5;
+            if (status == kFastClears && full.full == 0u) return -6;
         }
+        const Eval &e = fast ? quick : full;
         std::memcpy(feats + 8 * s, e.f, sizeof e.f);
-        terminal[s] = (uint8_t)e.terminal;
-        ncleared[s] = popc32(e.full);
-        anchor[s] = e.a;
+        terminal[s] = (uint8_t)full.terminal;
+        ncleared[s] = popc32(full.full);
+        anchor[s] = full.a;
         used_fast[s] = fast;
         uint32_t wo[S::NW];
         cols_to_rows<C, R>(nc, wo);
         for (int r = 0; r < S::N; ++r) rows_out[s * S::N + r] = (uint16_t)(wo[r >> 1] >> (16 * (r & 1)));
-        // placement_valid must agree with the terminal flag
-        if (placement_valid<C, R>(col, d, c) != (e.terminal == 0)) return -1;
-        if (term_fast[s] && !(e.terminal && e.full == 0u)) return -3;     // kFastTerminal must mean terminal, no clear
+        // placement_valid (heights + full-row count only) must agree with the terminal flag
+        if (hmax <= R && placement_valid<C, R>(col, d, c, hmax) != (full.terminal == 0)) return -1;
     }
     return n;
 }

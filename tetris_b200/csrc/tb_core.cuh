@@ -455,92 +455,9 @@ TB_HD void eval_slow(const uint32_t *col, uint32_t d, int c, Eval &e, uint32_t *
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-env record for incremental evaluation.  Built once per env (build_env), read by every
-// placement of that env (eval_fast).  Flat uint32 words so it can live in shared memory.
-// ---------------------------------------------------------------------------------------------
-template <int C, int R>
-struct Rec {
-    static constexpr int COLX = 0;                        // C+4 words: colx[k] = column k-2 (walls at -1, C)
-    static constexpr int PAND = COLX + C + 4;             // C+1 words: AND of columns < c
-    static constexpr int SAND = PAND + C + 1;             // C+1 words: AND of columns >= c
-    static constexpr int HPACK = SAND + C + 1;            // 2 words: 5-bit heights, entry k = column k-1
-    static constexpr int NRUNS = HPACK + 2;               // 2 words: 4-bit hole-run counts per column
-    static constexpr int PW = NRUNS + 2;                  // (C+1) u16: prefix sums of per-column wells
-    static constexpr int PRT = PW + (C + 2) / 2;          // (C+1) u16: prefix sums of per-column row transitions
-    static constexpr int TOT = PRT + (C + 2) / 2;         // ct, hd, wells, rt, holes, hole-row mask, hmax
-    static constexpr int T_CT = TOT + 0, T_HD = TOT + 1, T_WELLS = TOT + 2, T_RT = TOT + 3,
-                         T_HOLES = TOT + 4, T_HM = TOT + 5, T_HMAX = TOT + 6;
-    static constexpr int WORDS_RAW = TOT + 7;
-    static constexpr int WORDS = WORDS_RAW | 1;           // odd stride: conflict-free across envs
-};
-
-TB_HD uint32_t get_u16(const uint32_t *base, int i) { return (base[i >> 1] >> (16 * (i & 1))) & 0xffffu; }
-
-template <int C, int R>
-TB_HD void build_env(const uint32_t *col, uint32_t *rec)
-{
-    using S = Shape<C, R>;
-    using K = Rec<C, R>;
-    rec[K::COLX + 0] = 0u; rec[K::COLX + 1] = S::ALL;
-#pragma unroll
-    for (int c = 0; c < C; ++c) rec[K::COLX + 2 + c] = col[c];
-    rec[K::COLX + C + 2] = S::ALL; rec[K::COLX + C + 3] = 0u;
-    uint32_t acc = S::ALL;
-#pragma unroll
-    for (int c = 0; c < C; ++c) { rec[K::PAND + c] = acc; acc &= col[c]; }
-    rec[K::PAND + C] = acc;
-    acc = S::ALL;
-    rec[K::SAND + C] = acc;
-#pragma unroll
-    for (int c = C - 1; c >= 0; --c) { acc &= col[c]; rec[K::SAND + c] = acc; }
-
-    uint64_t hp = (uint64_t)R, nrp = 0;
-    int holes = 0, ct = 0, hd = 0, wells = 0, rt = 0, hmax = 0;
-    uint32_t hm = 0, L = S::ALL;
-    int hL = R;
-    uint32_t pw[(C + 2) / 2], prt[(C + 2) / 2];
-#pragma unroll
-    for (int i = 0; i < (C + 2) / 2; ++i) { pw[i] = 0; prt[i] = 0; }
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const uint32_t x = col[c];
-        const int h = height_of(x);
-        const uint32_t Rt = (c + 1 < C) ? col[c + 1] : S::ALL;
-        const int hR = (c + 1 < C) ? height_of(col[c + 1]) : R;
-        const uint32_t mh = mask_lo(h);
-        const uint32_t hole = ~x & mh;
-        holes += popc32(hole);
-        hm |= hole;
-        uint32_t t = hole & (x >> 1);
-        const int nr = popc32(t);
-        ct += 1 + 2 * nr;
-        while (t) { const int r = ctz32(t); hd += popc32(x >> (r + 1)); t &= t - 1; }
-        const int lim = imax(h, imin(hL, hR));
-        wells += run_sum(L & Rt & ~x & mask_lo(lim));
-        if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh);
-        else rt += popc32(L & mask_lo(hL));
-        hp |= (uint64_t)h << (5 * (c + 1));
-        nrp |= (uint64_t)nr << (4 * c);
-        pw[(c + 1) >> 1] |= (uint32_t)wells << (16 * ((c + 1) & 1));
-        prt[(c + 1) >> 1] |= (uint32_t)rt << (16 * ((c + 1) & 1));
-        hmax = imax(hmax, h);
-        L = x; hL = h;
-    }
-    hp |= (uint64_t)R << (5 * (C + 1));
-    rt += R - popc32(col[C - 1]);
-    rec[K::HPACK] = (uint32_t)hp; rec[K::HPACK + 1] = (uint32_t)(hp >> 32);
-    rec[K::NRUNS] = (uint32_t)nrp; rec[K::NRUNS + 1] = (uint32_t)(nrp >> 32);
-#pragma unroll
-    for (int i = 0; i < (C + 2) / 2; ++i) { rec[K::PW + i] = pw[i]; rec[K::PRT + i] = prt[i]; }
-    rec[K::T_CT] = (uint32_t)ct; rec[K::T_HD] = (uint32_t)hd; rec[K::T_WELLS] = (uint32_t)wells;
-    rec[K::T_RT] = (uint32_t)rt; rec[K::T_HOLES] = (uint32_t)holes; rec[K::T_HM] = hm;
-    rec[K::T_HMAX] = (uint32_t)hmax;
-}
-
-// ---------------------------------------------------------------------------------------------
 // run-sum by table.  A well mask of a non-terminal board has bits only below row R, so it splits into two halves
-// of HB = ceil(R / 2) bits; the table has 2^HB uint16 entries, entry for a half m = run_sum(m) | trail << 7 |
-// lead << 11 where trail / lead = length of the run of ones touching the half's bit 0 / bit HB-1.  A column is two
+// of HB = ceil(R / 2) bits; the table has 2^HB uint16 entries, entry for a half m = run_sum(m) | trail << 8 |
+// lead << 12 where trail / lead = length of the run of ones touching the half's bit 0 / bit HB-1.  A column is two
 // lookups plus the cross term of a run spanning the halves: (p+q)(p+q+1)/2 = p(p+1)/2 + q(q+1)/2 + p*q.
 // No POPC, no data-dependent loop.
 // ---------------------------------------------------------------------------------------------
@@ -558,110 +475,283 @@ TB_HD uint16_t run_tab_entry(uint32_t m)
     int trail = 0, lead = 0;
     while (trail < HB && ((m >> trail) & 1u)) ++trail;
     while (lead < HB && ((m >> (HB - 1 - lead)) & 1u)) ++lead;
-    return (uint16_t)(rs | (trail << 7) | (lead << 11));
+    return (uint16_t)(rs | (trail << 8) | (lead << 12));
 }
 template <int R>
 TB_HD int run_sum_tab(const uint16_t *tab, uint32_t w)   // w < 2^R
 {
     constexpr int HB = RunTab<R>::HB;
     const uint32_t e0 = tab[w & (uint32_t)(RunTab<R>::SIZE - 1)], e1 = tab[w >> HB];
-    return (int)((e0 & 127u) + (e1 & 127u) + (e0 >> 11) * ((e1 >> 7) & 15u));
+    return (int)(((e0 + e1) & 127u) + (e0 >> 12) * ((e1 >> 8) & 15u));   // run sums of the halves total < 128
 }
 
-// small non-negative int -> float without the (quarter-rate) I2F conversion unit
-TB_HD float u2f(int v)
+// Small non-negative int -> float without the conversion unit: the bit pattern 0x4B000000 + v is the float
+// 2^23 + v.  The env record keeps its totals already biased, so adding a placement's integer delta yields the
+// float bits directly and only the subtraction of 2^23 remains.
+constexpr uint32_t kFloatBias = 0x4B000000u;
+TB_HD float unbias(uint32_t bits)
 {
 #if defined(__CUDA_ARCH__)
-    return __int_as_float(0x4B000000 | v) - 8388608.0f;
+    return __uint_as_float(bits) - 8388608.0f;
 #else
-    return (float)v;
+    float f;
+    __builtin_memcpy(&f, &bits, 4);
+    return f - 8388608.0f;
 #endif
 }
+TB_HD float u2f(int v) { return unbias(kFloatBias + (uint32_t)v); }
 
-// eval_fast status
-constexpr int kFastDone = 0;      // features written, afterstate is legal
-constexpr int kFastClears = 1;    // a line clears: needs the general path
-constexpr int kFastTerminal = 2;  // no line clears and the piece reaches row R: terminal afterstate
-
-// Fast path: placement that clears no line and stays below the top.  Only the piece's columns and
-// their neighbours are re-evaluated; everything else comes from the env record.  Branch-free.
-// Precondition: every column height of the current board is <= R (a non-terminal state).
+// ---------------------------------------------------------------------------------------------
+// Per-env record for incremental evaluation.  Built once per env (build_env), read by every placement of that
+// env (eval_placement).  Flat uint32 words so it can live in shared memory; neighbour arrays are padded with
+// wall / zero sentinels so a placement at any column needs no range checks.
+// ---------------------------------------------------------------------------------------------
 template <int C, int R>
-TB_HD int eval_fast(const uint32_t *rec, const uint16_t *runtab, uint32_t d, int c, Eval &e)
+struct Env {
+    static constexpr int COLX = 0;                         // C+4 words: [k] = column k-2; walls (ALL) at -1 and C, 0 at -2, C+1
+    static constexpr int PAND = COLX + C + 4;              // C+1 words: AND of columns < c
+    static constexpr int SAND = PAND + C + 1;              // C+1 words: AND of columns >= c
+    static constexpr int H8 = SAND + C + 1;                // C+2 bytes: [k] = height of column k-1 (walls: R)
+    static constexpr int NR8 = H8 + (C + 2 + 3) / 4;       // C bytes: hole runs per column
+    static constexpr int PW16 = NR8 + (C + 3) / 4;         // C+3 u16: [i] = wells of columns < clamp(i-1, 0, C)
+    static constexpr int PRT16 = PW16 + (C + 3 + 1) / 2;   // C+2 u16: [i] = row transitions of columns < min(i, C)
+    static constexpr int TOT = PRT16 + (C + 2 + 1) / 2;    // ct, hd, wells, rt, holes (each + kFloatBias), hole-row mask, hmax
+    static constexpr int T_CT = TOT + 0, T_HD = TOT + 1, T_WELLS = TOT + 2, T_RT = TOT + 3,
+                         T_HOLES = TOT + 4, T_HM = TOT + 5, T_HMAX = TOT + 6;
+    static constexpr int WORDS_RAW = TOT + 7;
+    static constexpr int WORDS = WORDS_RAW | 1;            // odd stride: records of different envs spread over banks
+};
+
+// Precondition: every column height is <= R (a non-terminal state).
+template <int C, int R>
+TB_HD void build_env(const uint32_t *col, const uint16_t *runtab, uint32_t *rec)
 {
     using S = Shape<C, R>;
-    using K = Rec<C, R>;
-    const int w = desc_w(d);
-    const uint64_t hp = (uint64_t)rec[K::HPACK] | ((uint64_t)rec[K::HPACK + 1] << 32);
-    const uint32_t hw = (uint32_t)(hp >> (5 * c));                 // entry k = height of column c-1+k
-    const uint64_t nrp = (uint64_t)rec[K::NRUNS] | ((uint64_t)rec[K::NRUNS + 1] << 32);
-    const uint32_t nrw = (uint32_t)(nrp >> (4 * c));               // entry dx = hole runs of column c+dx
-
-    int nh[6];                                                     // heights of columns c-1 .. c+4
+    using K = Env<C, R>;
+    rec[K::COLX + 0] = 0u; rec[K::COLX + 1] = S::ALL;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) nh[k] = (int)((hw >> (5 * k)) & 31u);
+    for (int c = 0; c < C; ++c) rec[K::COLX + 2 + c] = col[c];
+    rec[K::COLX + C + 2] = S::ALL; rec[K::COLX + C + 3] = 0u;
+    uint32_t acc = S::ALL;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { rec[K::PAND + c] = acc; acc &= col[c]; }
+    rec[K::PAND + C] = acc;
+    acc = S::ALL;
+    rec[K::SAND + C] = acc;
+#pragma unroll
+    for (int c = C - 1; c >= 0; --c) { acc &= col[c]; rec[K::SAND + c] = acc; }
+
+    constexpr int NH = (C + 2 + 3) / 4, NN = (C + 3) / 4, NPW = (C + 3 + 1) / 2, NPR = (C + 2 + 1) / 2;
+    uint32_t h8[NH], nr8[NN], pw[NPW], prt[NPR];
+#pragma unroll
+    for (int i = 0; i < NH; ++i) h8[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) nr8[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NPW; ++i) pw[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NPR; ++i) prt[i] = 0;
+    h8[0] = (uint32_t)R;
+    h8[(C + 1) >> 2] |= (uint32_t)R << (8 * ((C + 1) & 3));
+    int holes = 0, ct = 0, hd = 0, wells = 0, rt = 0;
+    uint32_t hm = 0, L = S::ALL, any = 0;
+    int hL = R;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const uint32_t x = col[c];
+        const int h = height_of(x);
+        const uint32_t Rt = (c + 1 < C) ? col[c + 1] : S::ALL;
+        const uint32_t mh = mask_lo(h);
+        const uint32_t hole = ~x & mh;
+        holes += popc32(hole);
+        hm |= hole;
+        any |= x;
+        uint32_t t = hole & (x >> 1);
+        const int nr = popc32(t);
+        ct += 1 + 2 * nr;
+        while (t) { const int r = ctz32(t); hd += popc32(x >> (r + 1)); t &= t - 1; }
+        // heights <= R: the well cells of the column are exactly ~x & L & Rt (state.py:222-233,256-272)
+        wells += run_sum_tab<R>(runtab, L & Rt & ~x);
+        if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh);
+        else rt += popc32(L & mask_lo(hL));
+        h8[(c + 1) >> 2] |= (uint32_t)h << (8 * ((c + 1) & 3));
+        nr8[c >> 2] |= (uint32_t)nr << (8 * (c & 3));
+        // PW16[i] = wells of columns < clamp(i-1, 0, C): after column c the running sum belongs at i = c + 2
+        pw[(c + 2) >> 1] |= (uint32_t)wells << (16 * ((c + 2) & 1));
+        prt[(c + 1) >> 1] |= (uint32_t)rt << (16 * ((c + 1) & 1));
+        L = x; hL = h;
+    }
+    pw[(C + 2) >> 1] |= (uint32_t)wells << (16 * ((C + 2) & 1));     // i = C + 2 clamps to C
+    prt[(C + 1) >> 1] |= (uint32_t)rt << (16 * ((C + 1) & 1));       // i = C + 1 clamps to C
+    rt += R - popc32(col[C - 1]);
+#pragma unroll
+    for (int i = 0; i < NH; ++i) rec[K::H8 + i] = h8[i];
+#pragma unroll
+    for (int i = 0; i < NN; ++i) rec[K::NR8 + i] = nr8[i];
+#pragma unroll
+    for (int i = 0; i < NPW; ++i) rec[K::PW16 + i] = pw[i];
+#pragma unroll
+    for (int i = 0; i < NPR; ++i) rec[K::PRT16 + i] = prt[i];
+    rec[K::T_CT] = kFloatBias + (uint32_t)ct; rec[K::T_HD] = kFloatBias + (uint32_t)hd;
+    rec[K::T_WELLS] = kFloatBias + (uint32_t)wells; rec[K::T_RT] = kFloatBias + (uint32_t)rt;
+    rec[K::T_HOLES] = kFloatBias + (uint32_t)holes; rec[K::T_HM] = hm;
+    rec[K::T_HMAX] = (uint32_t)height_of(any);
+}
+
+// eval_placement status
+constexpr int kFastDone = 0;      // features written, afterstate is legal
+constexpr int kFastClears = 1;    // a line clears: features need the general path; e.a / e.full / e.terminal are set
+constexpr int kFastTerminal = 2;  // no line clears and the piece reaches row R: terminal afterstate
+
+// What a placement of width W at column c reads from the env record, independent of the orientation: shared by
+// the orientations of one column loop.
+template <int C, int R, int W>
+struct Neigh {
+    uint32_t y[W + 4];       // columns c-2 .. c+W+1
+    uint32_t frame;          // AND of the columns outside c .. c+W-1 (rows that are full but for the piece's columns)
+    uint32_t mh[W + 1];      // mask_lo(height) of columns c .. c+W
+    int h[W + 2];            // heights of columns c-1 .. c+W
+    int nr[W];               // hole runs of columns c .. c+W-1
+    uint32_t wells0, rt0;    // board totals (+ kFloatBias) minus the contributions of the columns the placement can change
+};
+template <int C, int R, int W>
+TB_HD void load_neigh(const uint32_t *rec, int c, Neigh<C, R, W> &nb)
+{
+    using K = Env<C, R>;
+    const uint8_t *rb = reinterpret_cast<const uint8_t *>(rec);
+    const uint16_t *rh = reinterpret_cast<const uint16_t *>(rec);
+#pragma unroll
+    for (int k = 0; k < W + 4; ++k) nb.y[k] = rec[K::COLX + c + k];
+#pragma unroll
+    for (int k = 0; k < W + 2; ++k) nb.h[k] = (int)rb[4 * K::H8 + c + k];
+#pragma unroll
+    for (int k = 0; k < W; ++k) nb.nr[k] = (int)rb[4 * K::NR8 + c + k];
+#pragma unroll
+    for (int k = 0; k < W + 1; ++k) nb.mh[k] = mask_lo(nb.h[1 + k]);
+    nb.frame = rec[K::PAND + c] & rec[K::SAND + c + W];
+    nb.wells0 = rec[K::T_WELLS] - ((uint32_t)rh[2 * K::PW16 + c + W + 2] - (uint32_t)rh[2 * K::PW16 + c]);
+    nb.rt0 = rec[K::T_RT] - ((uint32_t)rh[2 * K::PRT16 + c + W + 1] - (uint32_t)rh[2 * K::PRT16 + c]);
+}
+
+// Orientation descriptor decoded into the values eval_neigh uses.  In the kernels the descriptor is warp-uniform
+// and is decoded in converged code, so these live in uniform registers and cost no vector-ALU work.
+struct OriU {
+    int bot[4], len[4], top[4];   // per piece column: lowest cell offset, cell count, bot + len
+    uint32_t seg[4];              // mask_lo(len) << bot: the column's cells relative to the anchor row
+    uint32_t mbot[4], mtop[4];    // mask_lo(bot), mask_lo(top)
+    uint32_t chgm;                // mask_lo(len(changed_lines))
+    int ph;                       // piece height
+    uint32_t lh2;                 // 2 + 2 * landing_height_bonus + kFloatBias
+};
+constexpr int kOriWords = 28;     // OriU as flat words: bot[4] len[4] top[4] seg[4] mbot[4] mtop[4] chgm ph lh2 pad
+TB_HD OriU decode_ori(uint32_t d)
+{
+    OriU u;
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+        u.bot[dx] = desc_bot(d, dx);
+        u.len[dx] = desc_len(d, dx);
+        u.top[dx] = u.bot[dx] + u.len[dx];
+        u.seg[dx] = mask_lo(u.len[dx]) << u.bot[dx];
+        u.mbot[dx] = mask_lo(u.bot[dx]);
+        u.mtop[dx] = mask_lo(u.top[dx]);
+    }
+    u.chgm = mask_lo(desc_chg(d));
+    u.ph = desc_ph(d);
+    u.lh2 = 2u + (uint32_t)desc_bonus2(d) + kFloatBias;
+    return u;
+}
+static_assert(sizeof(OriU) == 27 * 4, "OriU is 27 words");
+
+// Incremental evaluation of one placement: orientation `u` (width W) anchored at column c.  Only the piece's
+// columns and their neighbours are re-evaluated; everything else comes from the env record.  Branch-free apart
+// from the two early exits.
+template <int C, int R, int W>
+TB_HD int eval_neigh(const uint32_t *rec, const uint16_t *runtab, const Neigh<C, R, W> &nb, const OriU &u, int c, Eval &e)
+{
+    using K = Env<C, R>;
+    int h[W + 2];
+    uint32_t y[W + 4];
+#pragma unroll
+    for (int k = 0; k < W + 2; ++k) h[k] = nb.h[k];
+#pragma unroll
+    for (int k = 0; k < W + 4; ++k) y[k] = nb.y[k];
     int a = 0;
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx) {
-        const int len = desc_len(d, dx);
-        a = imax(a, len > 0 ? nh[1 + dx] - desc_bot(d, dx) : 0);
-    }
-    uint32_t y[8];                                                 // columns c-2 .. c+5 after the placement
+    for (int dx = 0; dx < W; ++dx) a = imax(a, h[1 + dx] - u.bot[dx]);          // tetromino.py: anchor_row = max(h - bottom)
+
+    const uint32_t ma = mask_lo(a);
+    int gapsum = 0, gapcnt = 0, hdadd = 0;
+    uint32_t gapor = 0, fp = nb.frame;
+    uint32_t mt[W];                                                // mask_lo(new height) of the piece columns
 #pragma unroll
-    for (int k = 0; k < 8; ++k) y[k] = rec[K::COLX + c + k];
-    int gapsum = 0, gapcnt = 0, hdadd = 0, lastlen = 0;
-    uint32_t gapor = 0, fp = S::ALL;
-#pragma unroll
-    for (int dx = 0; dx < 4; ++dx) {
-        const int len = desc_len(d, dx);
-        const bool on = len > 0;
-        const int lo = a + desc_bot(d, dx);
-        const int h = nh[1 + dx];
-        const int g = on ? lo - h : 0;                             // new holes under the piece in this column
-        y[2 + dx] |= mask_lo(len) << lo;                           // len == 0 adds nothing
-        fp &= on ? y[2 + dx] : S::ALL;
+    for (int dx = 0; dx < W; ++dx) {
+        const int len = u.len[dx], lo = a + u.bot[dx], hh = h[1 + dx];
+        const int g = lo - hh;                                     // new holes under the piece in this column
+        y[2 + dx] |= u.seg[dx] << a;
+        fp &= y[2 + dx];
         gapsum += g;
         gapcnt += (g > 0);
-        gapor |= on ? (mask_lo(lo) ^ mask_lo(h)) : 0u;
-        hdadd += len * ((int)((nrw >> (4 * dx)) & 15u) + (g > 0));
-        nh[1 + dx] = on ? lo + len : h;
-        lastlen = on ? len : lastlen;
+        gapor |= ((ma << u.bot[dx]) | u.mbot[dx]) ^ nb.mh[dx];     // rows hh .. lo-1
+        hdadd += len * (nb.nr[dx] + (g > 0));
+        h[1 + dx] = lo + len;
+        mt[dx] = (ma << u.top[dx]) | u.mtop[dx];
     }
-    const uint32_t full = rec[K::PAND + c] & rec[K::SAND + c + w] & fp & (mask_lo(desc_chg(d)) << a);
-    if (full != 0u) return kFastClears;
-    if (a + desc_ph(d) > R) return kFastTerminal;
+    const uint32_t full = fp & (u.chgm << a);
+    const int top = a + u.ph;
+    e.a = a; e.full = full;
+    if (full != 0u) {
+        // stack rows are contiguous, so clearing k rows lowers the tallest column by exactly k
+        e.terminal = (imax((int)rec[K::T_HMAX], top) - popc32(full)) > R;
+        return kFastClears;
+    }
+    if (top > R) { e.terminal = 1; return kFastTerminal; }
+    e.terminal = 0;
 
-    // wells over columns c-1 .. c+4, row transitions over columns c .. c+4 (clipped to the board)
-    const int wlo = imax(c - 1, 0), hi = imin(c + 4, C - 1);
-    int wells = (int)rec[K::T_WELLS] - (int)(get_u16(rec + K::PW, hi + 1) - get_u16(rec + K::PW, wlo));
-    int rt = (int)rec[K::T_RT] - (int)(get_u16(rec + K::PRT, hi + 1) - get_u16(rec + K::PRT, c));
+    // wells over columns c-1 .. c+W, row transitions over columns c .. c+W; the sentinels make the walls come out right
+    uint32_t wells = nb.wells0, rt = nb.rt0;
 #pragma unroll
-    for (int k = 1; k <= 6; ++k) {
-        const int j = c - 2 + k;
-        const uint32_t wm = (j >= 0 && j < C) ? (y[k - 1] & y[k + 1] & ~y[k]) : 0u;
-        wells += run_sum_tab<R>(runtab, wm);
+    for (int k = 1; k <= W + 2; ++k) wells += (uint32_t)run_sum_tab<R>(runtab, y[k - 1] & y[k + 1] & ~y[k]);
+#pragma unroll
+    for (int dx = 0; dx < W; ++dx) {                               // piece columns: height > 0
+        const int hj = h[1 + dx], hl = h[dx];
+        rt += (uint32_t)(imax(0, hl - hj) + popc32((y[2 + dx] ^ y[1 + dx]) & mt[dx]));
     }
-#pragma unroll
-    for (int k = 2; k <= 6; ++k) {
-        const int j = c - 2 + k;
-        const int hj = nh[k - 1], hl = nh[k - 2];
-        // hj > 0: step down from the left column + cells differing from it; hj == 0: the left column's cells
-        const uint32_t m = hj > 0 ? ((y[k] ^ y[k - 1]) & mask_lo(hj)) : y[k - 1];
+    {                                                              // right neighbour: a column, or the wall
+        const int hj = h[W + 1], hl = h[W];
+        const uint32_t m = hj > 0 ? ((y[W + 2] ^ y[W + 1]) & nb.mh[W]) : y[W + 1];
         const int v = popc32(m) + (hj > 0 ? imax(0, hl - hj) : 0);
-        rt += (j < C) ? v : 0;
+        rt += (uint32_t)((c + W < C) ? v : -u.len[W - 1]);         // wall term R - popc(col[C-1]) loses the new cells
     }
-    rt -= (c + w == C) ? lastlen : 0;                              // right-wall term R - popc(col[C-1])
-
-    e.a = a; e.full = 0u; e.terminal = 0;
-    e.f[0] = u2f(popc32(rec[K::T_HM] | gapor));
-    e.f[1] = u2f((int)rec[K::T_CT] + 2 * gapcnt);
-    e.f[2] = u2f((int)rec[K::T_HOLES] + gapsum);
-    e.f[3] = u2f(2 * (a + 1) + desc_bonus2(d)) * 0.5f;
-    e.f[4] = u2f(wells);
-    e.f[5] = u2f(rt);
+    e.f[0] = unbias(kFloatBias + (uint32_t)popc32(rec[K::T_HM] | gapor));
+    e.f[1] = unbias(rec[K::T_CT] + 2u * (uint32_t)gapcnt);
+    e.f[2] = unbias(rec[K::T_HOLES] + (uint32_t)gapsum);
+    e.f[3] = unbias(2u * (uint32_t)a + u.lh2) * 0.5f;
+    e.f[4] = unbias(wells);
+    e.f[5] = unbias(rt);
     e.f[6] = 0.0f;
-    e.f[7] = u2f((int)rec[K::T_HD] + hdadd);
+    e.f[7] = unbias(rec[K::T_HD] + (uint32_t)hdadd);
     return kFastDone;
+}
+
+template <int C, int R, int W>
+TB_HD int eval_placement(const uint32_t *rec, const uint16_t *runtab, uint32_t d, int c, Eval &e)
+{
+    Neigh<C, R, W> nb;
+    load_neigh<C, R, W>(rec, c, nb);
+    return eval_neigh<C, R, W>(rec, runtab, nb, decode_ori(d), c, e);
+}
+
+// width dispatch (W is warp-uniform in the kernels)
+template <int C, int R>
+TB_HD int eval_placement_w(const uint32_t *rec, const uint16_t *runtab, uint32_t d, int c, Eval &e)
+{
+    switch (desc_w(d)) {
+    case 1: return eval_placement<C, R, 1>(rec, runtab, d, c, e);
+    case 2: return eval_placement<C, R, 2>(rec, runtab, d, c, e);
+    case 3: return eval_placement<C, R, 3>(rec, runtab, d, c, e);
+    default: return eval_placement<C, R, 4>(rec, runtab, d, c, e);
+    }
 }
 
 // Tetris.fitness (game.py:109-120): float32 products and sums, left to right, no FMA contraction.
@@ -679,20 +769,29 @@ TB_HD float fitness(const float *f, const float *w)
 #endif
 }
 
-// Is the placement a legal action, i.e. a non-terminal afterstate (game.py:69)?  Cheap in the common
-// case (heights only); falls back to an exact place-and-clear when the piece reaches row R.
-// Precondition: the current board has no cell in rows >= R.
+// Is the placement a legal action, i.e. a non-terminal afterstate (game.py:69)?  Stack rows are contiguous, so
+// clearing k rows lowers the tallest column by exactly k: terminal <=> max(hmax, a + piece height) - k > R.
+// hmax = tallest column of the current board.  Precondition: hmax <= R.
 template <int C, int R>
-TB_HD bool placement_valid(const uint32_t *col, uint32_t d, int c)
+TB_HD bool placement_valid(const uint32_t *col, uint32_t d, int c, int hmax)
 {
+    using S = Shape<C, R>;
     const int a = anchor_from_cols<C>(col, d, c);
-    if (a + desc_ph(d) <= R) return true;
-    uint32_t nc[C];
+    const int top = imax(hmax, a + desc_ph(d));
+    if (top <= R) return true;
+    uint32_t full = S::ALL;
 #pragma unroll
-    for (int k = 0; k < C; ++k) nc[k] = col[k];
-    int aa, term; uint32_t full;
-    place_and_clear<C, R>(nc, d, c, aa, full, term);
-    return term == 0;
+    for (int k = 0; k < C; ++k) {
+        const unsigned dx = (unsigned)(k - c);
+        uint32_t x = col[k];
+        if (dx < 4u) {
+            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+            x |= mask_lo((int)(f >> 2)) << (a + (int)(f & 3u));
+        }
+        full &= x;
+    }
+    full &= mask_lo(desc_chg(d)) << a;
+    return top - popc32(full) <= R;
 }
 
 // State.__init__ on a caller-supplied board (state.py:5-38): clear the full rows among the `chg` changed lines

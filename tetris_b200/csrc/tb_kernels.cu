@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/tetris_b200.h"
@@ -119,12 +120,13 @@ __device__ __forceinline__ int max_height(const uint32_t *col)
 template <int C, int R>
 __device__ __forceinline__ bool any_valid(const uint32_t *col, uint32_t pw, const uint32_t *s_ori)
 {
-    if (max_height<C>(col) + 4 <= R) return true;       // every piece is at most 4 rows tall
+    const int hmax = max_height<C>(col);
+    if (hmax + 4 <= R) return true;                     // every piece is at most 4 rows tall
     const int n = piece_num_slots(pw, C);
     for (int s = 0; s < n; ++s) {
         int ori, c;
         slot_to_placement(pw, C, s, ori, c);
-        if (placement_valid<C, R>(col, s_ori[ori], c)) return true;
+        if (placement_valid<C, R>(col, s_ori[ori], c, hmax)) return true;
     }
     return false;
 }
@@ -133,12 +135,13 @@ template <int C, int R>
 __device__ __forceinline__ unsigned long long valid_mask(const uint32_t *col, uint32_t pw, const uint32_t *s_ori)
 {
     const int n = piece_num_slots(pw, C);
-    if (max_height<C>(col) + 4 <= R) return (1ull << n) - 1ull;
+    const int hmax = max_height<C>(col);
+    if (hmax + 4 <= R) return (1ull << n) - 1ull;
     unsigned long long m = 0;
     for (int s = 0; s < n; ++s) {
         int ori, c;
         slot_to_placement(pw, C, s, ori, c);
-        if (placement_valid<C, R>(col, s_ori[ori], c)) m |= 1ull << s;
+        if (placement_valid<C, R>(col, s_ori[ori], c, hmax)) m |= 1ull << s;
     }
     return m;
 }
@@ -177,152 +180,208 @@ k_reset(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1 afterstates
+// K1 afterstates.
+//
+// A CTA owns a tile of TILE = 256 envs.  Phase A (thread per env): load + transpose the board, build the env
+// record in shared memory, append the env to the list of its piece.  Phase B (warp per window): all lanes of a
+// warp work on envs holding the SAME piece -- lane = (env k of the window, anchor column c) -- and walk the piece's
+// orientations in a warp-uniform loop, so the orientation descriptor is uniform, every loop over the piece's
+// columns has a uniform trip count, and the neighbourhood loads are shared by the orientations of a column loop.
+// Placements that clear a line only need the general evaluation for their FEATURES (legality follows from the
+// full-row count); they go to a CTA-wide queue and are evaluated one thread per item in phase S.
 // ---------------------------------------------------------------------------------------------
-template <int C, int R>
-struct TileSmem {
-    using K = Rec<C, R>;
-    uint32_t rec[32 * K::WORDS];
-    unsigned long long acc[32];      // K1: legal-slot bits set by the slow path; K3: best (score, slot) key per env
-    uint16_t pref[34];
-    uint16_t queue[64];
-    uint8_t pid[32];
-};
+constexpr int TILE = 256;
+constexpr int NWARPS = TILE / 32;
+constexpr int QCAP = 512;
 
-// piece/orientation tables and the run-sum table into shared memory (one barrier)
-template <int R>
-__device__ __forceinline__ void stage_all(uint32_t *s_ori, uint32_t *s_piece, uint16_t *s_run)
+template <int C, int R>
+struct CtaSmem {
+    using K = Env<C, R>;
+    uint32_t rec[TILE * K::WORDS];
+    uint32_t odesc[kNumOris][kOriWords]; // orientation descriptors, decoded (OriU): broadcast 128-bit loads
+    uint32_t vloc[TILE][2];              // K1: legal placements of each env per column loop, loop-local bit c * n + o
+                                         // K3: best orderable score of each env per column loop
+    uint16_t queue[QCAP];                // line-clearing placements: env << 6 | slot
+    uint16_t run[RunTab<R>::SIZE];
+    uint8_t list[kNumPieces][TILE];      // tile-local env indices grouped by piece
+    uint8_t pid[TILE];                   // piece of each env of the tile
+    uint8_t bslot[TILE][2];              // K3: slot of the best score per column loop
+    int cnt[kNumPieces + 1];             // envs per piece; [kNumPieces] = queue length
+    uint32_t ori[32], piece[16];
+};
+// K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements
+struct BestSmem { unsigned long long best[TILE]; };
+
+template <int C, int R>
+__device__ __forceinline__ void stage_cta(CtaSmem<C, R> &sm)
 {
-    if (threadIdx.x < kNumOris) s_ori[threadIdx.x] = c_ori[threadIdx.x];
-    if (threadIdx.x < kNumPieces) s_piece[threadIdx.x] = c_piece[threadIdx.x];
-    for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) s_run[m] = run_tab_entry<R>((uint32_t)m);
+    if (threadIdx.x < kNumOris) {
+        sm.ori[threadIdx.x] = c_ori[threadIdx.x];
+        const OriU u = decode_ori(c_ori[threadIdx.x]);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&u);
+        for (int i = 0; i < 27; ++i) sm.odesc[threadIdx.x][i] = w[i];
+        sm.odesc[threadIdx.x][27] = 0u;
+    }
+    if (threadIdx.x < kNumPieces) sm.piece[threadIdx.x] = c_piece[threadIdx.x];
+    for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = run_tab_entry<R>((uint32_t)m);
     __syncthreads();
 }
 
-__device__ __forceinline__ void emit_features(float *__restrict__ feats, int64_t env, int a_stride, int slot,
-                                              const Eval &ev, const F8 &dirs)
+template <bool DIRS>
+__device__ __forceinline__ void emit_row(float *__restrict__ row, const Eval &ev, const F8 &dirs)
 {
-    float4 *dst = reinterpret_cast<float4 *>(feats + ((size_t)env * (size_t)a_stride + (size_t)slot) * 8);
-    dst[0] = make_float4(ev.f[0] * dirs.v[0], ev.f[1] * dirs.v[1], ev.f[2] * dirs.v[2], ev.f[3] * dirs.v[3]);
-    dst[1] = make_float4(ev.f[4] * dirs.v[4], ev.f[5] * dirs.v[5], ev.f[6] * dirs.v[6], ev.f[7] * dirs.v[7]);
+    float4 *dst = reinterpret_cast<float4 *>(row);
+    if (DIRS) {
+        dst[0] = make_float4(ev.f[0] * dirs.v[0], ev.f[1] * dirs.v[1], ev.f[2] * dirs.v[2], ev.f[3] * dirs.v[3]);
+        dst[1] = make_float4(ev.f[4] * dirs.v[4], ev.f[5] * dirs.v[5], ev.f[6] * dirs.v[6], ev.f[7] * dirs.v[7]);
+    } else {
+        dst[0] = make_float4(ev.f[0], ev.f[1], ev.f[2], ev.f[3]);
+        dst[1] = make_float4(ev.f[4], ev.f[5], ev.f[6], ev.f[7]);
+    }
+}
+__device__ __forceinline__ float *feat_row(float *__restrict__ feats, int64_t env, int a_stride, int slot)
+{
+    return feats + ((size_t)env * (size_t)a_stride + (size_t)slot) * 8;
 }
 
-// Flattened item list of a tile: item i belongs to the env whose slot range [pref[env], pref[env+1]) holds i.
-// `heads` has bit j set when item base+j is the first item of an env; `cum` = envs that start before `base`.
-__device__ __forceinline__ uint32_t window_heads(int own_lo, int own_n, int base)
+// Append `packed` of the flagged lanes to the CTA queue (one shared atomic per warp).  Returns false for a lane
+// whose item did not fit (the caller evaluates it in place).
+template <int C, int R>
+__device__ __forceinline__ bool queue_push(CtaSmem<C, R> &sm, bool flag, uint32_t packed, int lane)
 {
-    const unsigned rel = (unsigned)(own_lo - base);
-    return __reduce_or_sync(FULLMASK, (own_n > 0 && rel < 32u) ? (1u << rel) : 0u);
-}
-// bits of a per-item ballot that fall into the owner lane's slot range, moved to slot positions
-__device__ __forceinline__ unsigned long long window_bits(uint32_t bal, int own_lo, int own_hi, int base)
-{
-    const int s = imax(own_lo, base), t = imin(own_hi, base + 32);
-    if (s >= t) return 0ull;
-    const uint32_t bits = (bal >> (s - base)) & (0xFFFFFFFFu >> (32 - (t - s)));
-    return (unsigned long long)bits << (s - own_lo);
+    const unsigned bal = __ballot_sync(FULLMASK, flag);
+    if (bal == 0u) return true;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&sm.cnt[kNumPieces], __popc(bal));
+    base = __shfl_sync(FULLMASK, base, 0);
+    if (!flag) return true;
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    if (pos >= QCAP) return false;
+    sm.queue[pos] = (uint16_t)packed;
+    return true;
 }
 
-template <int C, int R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int V> struct IntC { static constexpr int value = V; };
+
+// general (from-scratch) evaluation kept out of line: it is the rare path and would otherwise be inlined per orientation
+template <int C, int R>
+__device__ __noinline__ void eval_slow_outofline(const uint32_t *col, uint32_t d, int c, Eval *ev)
+{
+    eval_slow<C, R>(col, d, c, *ev, nullptr);
+}
+
+// lane -> (env k of the window, column c); envs per window
+template <int C> struct Win { static constexpr int EPW = 32 / C; };
+
+template <int C, int R, bool DIRS, int MINB>
+__global__ void __launch_bounds__(TILE, MINB)
 k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
               int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
 {
-    using K = Rec<C, R>;
-    __shared__ TileSmem<C, R> s_tile[WARPS];
-    __shared__ uint32_t s_ori[32], s_piece[16];
-    __shared__ uint16_t s_run[RunTab<R>::SIZE];
-    stage_all<R>(s_ori, s_piece, s_run);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lane_le = (2u << lane) - 1u;
-    TileSmem<C, R> &sm = s_tile[warp];
-    uint32_t *acc32 = reinterpret_cast<uint32_t *>(sm.acc);
-    const int64_t n_tiles = (sv.n_env + 31) >> 5;
+    using K = Env<C, R>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaSmem<C, R> &sm = *reinterpret_cast<CtaSmem<C, R> *>(smem_raw);
+    stage_cta(sm);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool want_terminal = (flags & TB_FLAG_INCLUDE_TERMINAL) != 0;
+    const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
 
-    for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * WARPS) {
-        const int64_t e0 = tile * 32, e = e0 + lane;
-        // ---- phase A: one lane per env: load, transpose, build the env record
-        int n_slots = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t e0 = tile * TILE, e = e0 + tid;
+        if (tid <= kNumPieces) sm.cnt[tid] = 0;
+        __syncthreads();                                   // also: the previous tile is done with rec / queue / vloc
+        // ---- phase A
+        sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
         if (e < sv.n_env) {
             uint32_t col[C];
             load_board<C, R>(sv, e, col);
             const Meta mt = unpack_meta(sv.meta[e]);
-            build_env<C, R>(col, sm.rec + lane * K::WORDS);
-            sm.pid[lane] = (uint8_t)mt.piece;
-            n_slots = piece_num_slots(s_piece[mt.piece], C);
+            build_env<C, R>(col, sm.run, sm.rec + tid * K::WORDS);
+            sm.list[mt.piece][atomicAdd(&sm.cnt[mt.piece], 1)] = (uint8_t)tid;
+            sm.pid[tid] = (uint8_t)mt.piece;
         }
-        sm.acc[lane] = 0ull;
-        int incl = n_slots;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULLMASK, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int own_lo = incl - n_slots, own_hi = incl;
-        sm.pref[lane] = (uint16_t)own_lo;
-        const int total = __shfl_sync(FULLMASK, incl, 31);
-        __syncwarp();
-
-        // ---- phase B: one lane per (env, slot) item
-        auto slow_item = [&](uint32_t packed) {
-            const int env = (int)(packed >> 8), slot = (int)(packed & 0xffu);
-            int ori, c;
-            slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
-            Eval ev;
-            eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, s_ori[ori], c, ev, nullptr);
-            if (!ev.terminal || want_terminal) emit_features(feats, e0 + env, a_stride, slot, ev, dirs);
-            if (!ev.terminal) atomicOr(&acc32[2 * env + (slot >> 5)], 1u << (slot & 31));
+        __syncthreads();
+        // ---- phase B: per piece, per column loop of the piece; a window = EPW envs x (C - W + 1) columns
+        auto column_loop = [&](auto wtag, int p, int np, int l, int n, int ob, int sbase) {
+            constexpr int W = decltype(wtag)::value;
+            constexpr int NC = C - W + 1, EPW = 32 / NC;
+            const int k = lane / NC, c = lane - k * NC;
+            const bool lane_ok = k < EPW;
+            const uint32_t segmask = lane_ok ? (((1u << NC) - 1u) << (k * NC)) : 0u;
+            const int nwin = (np + EPW - 1) / EPW;
+            for (int win = (warp + p + 3 * l) & (NWARPS - 1); win < nwin; win += NWARPS) {
+                const int idx = win * EPW + k;
+                const bool on = lane_ok && idx < np;
+                const int env = on ? (int)sm.list[p][idx] : 0;
+                const uint32_t *rec = sm.rec + env * K::WORDS;
+                Neigh<C, R, W> nb;
+                load_neigh<C, R, W>(rec, c, nb);
+                float *row = feat_row(feats, e0 + env, a_stride, sbase + c * n);
+                uint32_t vbits = 0u;
+#pragma unroll 1
+                for (int o = 0; o < n; ++o) {
+                    const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[ob + o]);
+                    const int slot = sbase + c * n + o;
+                    bool slow = false;
+                    if (on) {
+                        Eval ev;
+                        const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
+                        if (status == kFastDone) emit_row<DIRS>(row + 8 * o, ev, dirs);
+                        else if (status == kFastClears) slow = !ev.terminal || want_terminal;
+                        else slow = want_terminal;
+                        if (!ev.terminal) vbits |= 1u << (c * n + o);
+                    }
+                    if (!queue_push(sm, slow, (uint32_t)(env << 6 | slot), lane)) {
+                        Eval e2;                            // queue full: evaluate in place
+                        eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[ob + o], c, &e2);
+                        emit_row<DIRS>(row + 8 * o, e2, dirs);
+                    }
+                }
+                if (on) {
+                    const uint32_t v = __reduce_or_sync(segmask, vbits);
+                    if (c == 0) sm.vloc[env][l] = v;
+                }
+            }
         };
-        unsigned long long vmask = 0ull;                   // owner lane: legal-slot mask of its env
-        int qn = 0, cum = 0;                               // warp-uniform: queue length, envs started before base
-        for (int base = 0; base < total; base += 32) {
-            const uint32_t heads = window_heads(own_lo, n_slots, base);
-            const int i = base + lane;
-            bool slow = false, ok = false;
-            uint32_t packed = 0;
-            if (i < total) {
-                const int env = cum + __popc(heads & lane_le) - 1;
-                const int slot = i - (int)sm.pref[env];
-                int ori, c;
-                slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
-                Eval ev;
-                const int status = eval_fast<C, R>(sm.rec + env * K::WORDS, s_run, s_ori[ori], c, ev);
-                if (status == kFastDone) {
-                    emit_features(feats, e0 + env, a_stride, slot, ev, dirs);
-                    ok = true;
-                } else if (status == kFastClears || want_terminal) {
-                    slow = true;
-                    packed = (uint32_t)(env << 8 | slot);
-                }
-            }
-            cum += __popc(heads);
-            vmask |= window_bits(__ballot_sync(FULLMASK, ok), own_lo, own_hi, base);
-            const unsigned bal = __ballot_sync(FULLMASK, slow);
-            if (bal) {
-                if (slow) sm.queue[qn + __popc(bal & (lane_le >> 1))] = (uint16_t)packed;
-                qn += __popc(bal);
-                __syncwarp();
-                if (qn >= 32) {
-                    slow_item(sm.queue[lane]);
-                    __syncwarp();
-                    uint16_t mv = 0;
-                    if (lane < qn - 32) mv = sm.queue[32 + lane];
-                    __syncwarp();
-                    if (lane < qn - 32) sm.queue[lane] = mv;
-                    qn -= 32;
-                    __syncwarp();
+#pragma unroll 1
+        for (int p = 0; p < kNumPieces; ++p) {
+            const int np = sm.cnt[p];
+            if (np == 0) continue;
+            const uint32_t pw = sm.piece[p];
+            const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
+#pragma unroll 1
+            for (int l = 0; l < 2; ++l) {
+                const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase;
+                const int sbase = l ? n0 * (C - w0 + 1) : 0;
+                if (n == 0) break;
+                switch (w) {
+                case 1: column_loop(IntC<1>(), p, np, l, n, ob, sbase); break;
+                case 2: column_loop(IntC<2>(), p, np, l, n, ob, sbase); break;
+                case 3: column_loop(IntC<3>(), p, np, l, n, ob, sbase); break;
+                default: if (C >= 4) column_loop(IntC<4>(), p, np, l, n, ob, sbase); break;
                 }
             }
         }
-        if (lane < qn) slow_item(sm.queue[lane]);
-        __syncwarp();
+        __syncthreads();
+        // ---- phase S: line-clearing placements, one thread per item, general evaluation
+        const int qn = min(sm.cnt[kNumPieces], QCAP);
+        for (int i = tid; i < qn; i += TILE) {
+            const uint32_t packed = sm.queue[i];
+            const int env = (int)(packed >> 6), slot = (int)(packed & 63u);
+            int ori, cc;
+            slot_to_placement(sm.piece[sm.pid[env]], C, slot, ori, cc);
+            Eval ev;
+            eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[ori], cc, ev, nullptr);
+            emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs);
+        }
+        // ---- legal-action masks, thread per env (coalesced)
         if (e < sv.n_env) {
-            const unsigned long long v = vmask | sm.acc[lane];
+            const uint32_t pw = sm.piece[sm.pid[tid]];
+            const int s1 = (int)(pw & 3u) * (C - (int)((pw >> 2) & 7u) + 1);
+            const unsigned long long v = (unsigned long long)sm.vloc[tid][0] | ((unsigned long long)sm.vloc[tid][1] << s1);
             if (valid_out) valid_out[e] = v;
             if (count_out) count_out[e] = __popcll(v);
         }
-        __syncwarp();
     }
 }
 
@@ -394,7 +453,7 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
             if (action < n_slots) {
                 int ori, c;
                 slot_to_placement(pw, C, action, ori, c);
-                if (placement_valid<C, R>(col, s_ori[ori], c)) sel = action;
+                if (placement_valid<C, R>(col, s_ori[ori], c, max_height<C>(col))) sel = action;
             }
         } else {
             const unsigned long long vm = valid_mask<C, R>(col, pw, s_ori);   // game.py:69
@@ -561,27 +620,32 @@ __device__ __forceinline__ uint32_t orderable(float f)
     const uint32_t u = __float_as_uint(f + 0.0f);          // + 0.0f: -0.0 -> +0.0 (np.argmax treats them equal)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ unsigned long long score_key(uint32_t ord, int slot)
+{
+    return ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)slot);   // ties: lower slot
+}
 
-// greedy linear policy: warp tile of 32 envs; phases A (lane per env) / B (lane per afterstate) / C (lane per env)
-template <int C, int R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+// Greedy linear policy.  Same tile scheme as K1; a thread keeps its env's board in registers for all n_steps and
+// rebuilds the env record in shared memory every step.  Per step: A (thread per env) record + piece lists,
+// B (warp per window of same-piece envs) score every legal placement and keep the first arg-max per env,
+// S (thread per item) the line-clearing placements, C (thread per env) apply the chosen placement.
+template <int C, int R>
+__global__ void __launch_bounds__(TILE, 2)
 k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats)
 {
-    using K = Rec<C, R>;
-    __shared__ TileSmem<C, R> s_tile[WARPS];
-    __shared__ uint32_t s_ori[32], s_piece[16];
-    __shared__ uint16_t s_run[RunTab<R>::SIZE];
+    using K = Env<C, R>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaSmem<C, R> &sm = *reinterpret_cast<CtaSmem<C, R> *>(smem_raw);
+    BestSmem &bs = *reinterpret_cast<BestSmem *>(smem_raw + ((sizeof(CtaSmem<C, R>) + 15) & ~(size_t)15));
     __shared__ long long s_blk[TB_ST_COUNT];
-    stage_all<R>(s_ori, s_piece, s_run);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lane_le = (2u << lane) - 1u;
-    TileSmem<C, R> &sm = s_tile[warp];
-    const int64_t n_tiles = (sv.n_env + 31) >> 5;
+    stage_cta(sm);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
     LaneStats st;
     stats_zero(st);
 
-    for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * WARPS) {
-        const int64_t e = tile * 32 + lane;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t e = tile * TILE + tid;
         const bool active = e < sv.n_env;
         uint32_t col[C];
         Meta mt; mt.piece = 0; mt.bag = 0u; mt.draws = 0u;
@@ -594,117 +658,123 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             key = env_key(seed, (uint64_t)(env_offset + e));
         } else {
 #pragma unroll
-            for (int k = 0; k < C; ++k) col[k] = 0u;
+            for (int i = 0; i < C; ++i) col[i] = 0u;
         }
         for (int t = 0; t < n_steps; ++t) {
+            if (tid <= kNumPieces) sm.cnt[tid] = 0;
+            __syncthreads();                               // phase C / S of the previous step are done with smem
             // ---- phase A
-            int n_slots = 0;
+            sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
+            bs.best[tid] = 0ull;
             if (active) {
-                build_env<C, R>(col, sm.rec + lane * K::WORDS);
-                sm.pid[lane] = (uint8_t)mt.piece;
-                n_slots = piece_num_slots(s_piece[mt.piece], C);
-                st.afterstates += n_slots;
+                build_env<C, R>(col, sm.run, sm.rec + tid * K::WORDS);
+                sm.list[mt.piece][atomicAdd(&sm.cnt[mt.piece], 1)] = (uint8_t)tid;
+                sm.pid[tid] = (uint8_t)mt.piece;
+                st.afterstates += piece_num_slots(sm.piece[mt.piece], C);
             }
-            sm.acc[lane] = 0ull;
-            int incl = n_slots;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULLMASK, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int own_lo = incl - n_slots, own_hi = incl;
-            sm.pref[lane] = (uint16_t)own_lo;
-            const int total = __shfl_sync(FULLMASK, incl, 31);
-            __syncwarp();
-            // ---- phase B: score every legal afterstate, keep the first arg-max per env.
-            // Fast-path items: segmented max-scan over the window's lanes (items of an env are contiguous), the env's
-            // owner lane picks up the result of its segment.  Slow-path items (rare): 64-bit atomicMax in shared.
-            auto slow_item = [&](uint32_t packed) {
-                const int env = (int)(packed >> 8), slot = (int)(packed & 0xffu);
-                int ori, c;
-                slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
-                Eval ev;
-                eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, s_ori[ori], c, ev, nullptr);
-                if (!ev.terminal) {
-                    const float score = fitness(ev.f, wts.v);                   // game.py:109-120
-                    atomicMax(&sm.acc[env], ((unsigned long long)orderable(score) << 32) |
-                                                (unsigned long long)(0xFFFFFFFFu - (uint32_t)slot));
+            __syncthreads();
+            // ---- phase B: score every legal placement, keep the first arg-max per env and column loop
+            auto column_loop = [&](auto wtag, int p, int np, int l, int n, int ob, int sbase) {
+                constexpr int W = decltype(wtag)::value;
+                constexpr int NC = C - W + 1, EPW = 32 / NC;
+                const int k = lane / NC, c = lane - k * NC;
+                const bool lane_ok = k < EPW;
+                const uint32_t segmask = lane_ok ? (((1u << NC) - 1u) << (k * NC)) : 0u;
+                const int nwin = (np + EPW - 1) / EPW;
+                for (int win = (warp + p + 3 * l) & (NWARPS - 1); win < nwin; win += NWARPS) {
+                    const int idx = win * EPW + k;
+                    const bool on = lane_ok && idx < np;
+                    const int env = on ? (int)sm.list[p][idx] : 0;
+                    const uint32_t *rec = sm.rec + env * K::WORDS;
+                    Neigh<C, R, W> nb;
+                    load_neigh<C, R, W>(rec, c, nb);
+                    uint32_t best_ord = 0u;                // this lane's best orderable score (0 = none) and its slot
+                    int best_slot = 0;
+#pragma unroll 1
+                    for (int o = 0; o < n; ++o) {
+                        const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[ob + o]);
+                        const int slot = sbase + c * n + o;
+                        bool slow = false;
+                        if (on) {
+                            Eval ev;
+                            const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
+                            if (status == kFastDone) {
+                                const uint32_t ord = orderable(fitness(ev.f, wts.v));         // game.py:109-120
+                                if (ord > best_ord) { best_ord = ord; best_slot = slot; }     // slots ascend with o
+                            } else if (status == kFastClears) {
+                                slow = !ev.terminal;
+                            }
+                        }
+                        if (!queue_push(sm, slow, (uint32_t)(env << 6 | slot), lane)) {
+                            Eval e2;                        // queue full: evaluate in place
+                            eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[ob + o], c, &e2);
+                            atomicMax(&bs.best[env], score_key(orderable(fitness(e2.f, wts.v)), slot));
+                        }
+                    }
+                    if (on) {
+                        // first arg-max over the env's lanes: highest score, then lowest slot
+                        const uint32_t m = __reduce_max_sync(segmask, best_ord);
+                        const uint32_t sl = __reduce_min_sync(segmask, best_ord == m ? (uint32_t)best_slot : 255u);
+                        if (c == 0) { sm.vloc[env][l] = m; sm.bslot[env][l] = (uint8_t)sl; }
+                    }
                 }
             };
-            uint32_t best_key = 0u;                        // owner lane: best orderable score so far (0 = none)
-            int best_slot = 0;
-            int qn = 0, cum = 0;
-            for (int base = 0; base < total; base += 32) {
-                const uint32_t heads = window_heads(own_lo, n_slots, base);
-                const int i = base + lane;
-                bool slow = false;
-                uint32_t packed = 0, key = 0u;
-                int slot = 0;
-                if (i < total) {
-                    const int env = cum + __popc(heads & lane_le) - 1;
-                    slot = i - (int)sm.pref[env];
-                    int ori, c;
-                    slot_to_placement(s_piece[sm.pid[env]], C, slot, ori, c);
-                    Eval ev;
-                    const int status = eval_fast<C, R>(sm.rec + env * K::WORDS, s_run, s_ori[ori], c, ev);
-                    if (status == kFastDone) key = orderable(fitness(ev.f, wts.v));
-                    else if (status == kFastClears) { slow = true; packed = (uint32_t)(env << 8 | slot); }
-                }
-                cum += __popc(heads);
-                // lanes below this one that belong to the same env (its segment may have started in an earlier window)
-                const int dist = lane - (31 - __clz((int)(heads & lane_le)));
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t k2 = __shfl_up_sync(FULLMASK, key, o);
-                    const int s2 = __shfl_up_sync(FULLMASK, slot, o);
-                    if (o <= dist && o <= lane && k2 >= key) { key = k2; slot = s2; }   // ties: the earlier slot wins
-                }
-                const int seg_s = imax(own_lo, base), seg_t = imin(own_hi, base + 32);
-                const int src = seg_s < seg_t ? seg_t - 1 - base : lane;
-                const uint32_t k3 = __shfl_sync(FULLMASK, key, src);
-                const int s3 = __shfl_sync(FULLMASK, slot, src);
-                if (seg_s < seg_t && k3 > best_key) { best_key = k3; best_slot = s3; }   // earlier windows win ties
-                const unsigned bal = __ballot_sync(FULLMASK, slow);
-                if (bal) {
-                    if (slow) sm.queue[qn + __popc(bal & (lane_le >> 1))] = (uint16_t)packed;
-                    qn += __popc(bal);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        slow_item(sm.queue[lane]);
-                        __syncwarp();
-                        uint16_t mv = 0;
-                        if (lane < qn - 32) mv = sm.queue[32 + lane];
-                        __syncwarp();
-                        if (lane < qn - 32) sm.queue[lane] = mv;
-                        qn -= 32;
-                        __syncwarp();
+#pragma unroll 1
+            for (int p = 0; p < kNumPieces; ++p) {
+                const int np = sm.cnt[p];
+                if (np == 0) continue;
+                const uint32_t pw = sm.piece[p];
+                const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
+#pragma unroll 1
+                for (int l = 0; l < 2; ++l) {
+                    const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase;
+                    const int sbase = l ? n0 * (C - w0 + 1) : 0;
+                    if (n == 0) break;
+                    switch (w) {
+                    case 1: column_loop(IntC<1>(), p, np, l, n, ob, sbase); break;
+                    case 2: column_loop(IntC<2>(), p, np, l, n, ob, sbase); break;
+                    case 3: column_loop(IntC<3>(), p, np, l, n, ob, sbase); break;
+                    default: if (C >= 4) column_loop(IntC<4>(), p, np, l, n, ob, sbase); break;
                     }
                 }
             }
-            if (lane < qn) slow_item(sm.queue[lane]);
-            __syncwarp();
+            __syncthreads();
+            // ---- phase S
+            const int qn = min(sm.cnt[kNumPieces], QCAP);
+            for (int i = tid; i < qn; i += TILE) {
+                const uint32_t packed = sm.queue[i];
+                const int env = (int)(packed >> 6), slot = (int)(packed & 63u);
+                int ori, cc;
+                slot_to_placement(sm.piece[sm.pid[env]], C, slot, ori, cc);
+                Eval ev;
+                eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[ori], cc, ev, nullptr);
+                atomicMax(&bs.best[env], score_key(orderable(fitness(ev.f, wts.v)), slot));
+            }
+            __syncthreads();
             // ---- phase C
             if (active) {
-                unsigned long long best = sm.acc[lane];
-                if (best_key != 0u) {
-                    const unsigned long long k64 = ((unsigned long long)best_key << 32) |
-                                                   (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_slot);
-                    best = k64 > best ? k64 : best;
+                unsigned long long best = bs.best[tid];
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const uint32_t m = sm.vloc[tid][l];
+                    if (m != 0u) {
+                        const unsigned long long k64 = score_key(m, (int)sm.bslot[tid][l]);
+                        best = k64 > best ? k64 : best;
+                    }
                 }
                 if (best != 0ull) {
                     const int slot = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
-                    int ori, c;
-                    slot_to_placement(s_piece[mt.piece], C, slot, ori, c);
-                    apply_placement<C, R>(col, mt, ep, s_ori[ori], c, piece_set, key, s_ori, s_piece, st);
+                    int ori, cc;
+                    slot_to_placement(sm.piece[mt.piece], C, slot, ori, cc);
+                    apply_placement<C, R>(col, mt, ep, sm.ori[ori], cc, piece_set, key, sm.ori, sm.piece, st);
                 } else {
                     // no legal placement: only reachable from a caller-supplied dead state -> start a new episode
 #pragma unroll
-                    for (int k = 0; k < C; ++k) col[k] = 0u;
+                    for (int i = 0; i < C; ++i) col[i] = 0u;
                     mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
                     ep = make_uint2(0u, 0u);
                 }
             }
-            __syncwarp();
         }
         if (active) {
             store_board<C, R>(sv, e, col);
@@ -858,6 +928,22 @@ static int sm_count()
     }
     return cached > 0 ? cached : 148;
 }
+// tuning knobs read from the environment (experiments only; the defaults are what ships)
+static int tuning_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+// dynamic shared memory above 48 KB is opt-in per kernel
+static int opt_in_smem(const void *kernel, size_t bytes)
+{
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(shared memory %zu B): %s", bytes, cudaGetErrorString(e));
+        return -2;
+    }
+    return 0;
+}
 static unsigned grid_for(int64_t work_items, int per_block, int blocks_per_sm)
 {
     const int64_t need = (work_items + per_block - 1) / per_block;
@@ -959,12 +1045,17 @@ int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_
     if (a_stride < 1) return fail("%s: a_stride must be >= the piece set's slot count", __func__);
     cudaStream_t st = (cudaStream_t)stream;
     const F8 dirs = f8_from(directions, 1.0f);
-    constexpr int WARPS = 4;
+    const int minb = tuning_int("TB_K1_MINB", 3) == 2 ? 2 : 3;
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
-        k_afterstates<c, r, WARPS><<<grid_for((n_env + 31) / 32, WARPS, 8), WARPS * 32, 0, st>>>(        \
-            make_view<c, r>(state, n_env), feats_out, (unsigned long long *)valid_out, count_out, a_stride, dirs, \
-            flags);                                                                                      \
+        const size_t smem = sizeof(CtaSmem<c, r>);                                                       \
+        const unsigned grid = grid_for(n_env, TILE, minb);                                               \
+        void (*kern)(StateView, float *, unsigned long long *, int *, int, F8, int) =                    \
+            directions ? (minb == 2 ? k_afterstates<c, r, true, 2> : k_afterstates<c, r, true, 3>)       \
+                       : (minb == 2 ? k_afterstates<c, r, false, 2> : k_afterstates<c, r, false, 3>);    \
+        if (opt_in_smem((const void *)kern, smem)) return -2;                                            \
+        kern<<<grid, TILE, smem, st>>>(make_view<c, r>(state, n_env), feats_out,                         \
+                                       (unsigned long long *)valid_out, count_out, a_stride, dirs, flags); \
         return check_launch("tb_afterstates");                                                           \
     }
     TB_SHAPES(X)
@@ -1022,15 +1113,17 @@ int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uin
     if (policy != TB_POLICY_GREEDY && policy != TB_POLICY_RANDOM) return fail("%s: unknown policy", __func__);
     cudaStream_t st = (cudaStream_t)stream;
     const F8 wts = f8_from(weights, 0.0f);
-    constexpr int WARPS = 4;
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
         if (policy == TB_POLICY_RANDOM)                                                                  \
             k_rollout_random<c, r><<<grid_for(n_env, 128, 8), 128, 0, st>>>(make_view<c, r>(state, n_env), \
                 env_offset, seed, piece_set, n_steps, stats);                                            \
-        else                                                                                             \
-            k_rollout_greedy<c, r, WARPS><<<grid_for((n_env + 31) / 32, WARPS, 4), WARPS * 32, 0, st>>>( \
+        else {                                                                                           \
+            const size_t smem = ((sizeof(CtaSmem<c, r>) + 15) & ~(size_t)15) + sizeof(BestSmem);         \
+            if (opt_in_smem((const void *)k_rollout_greedy<c, r>, smem)) return -2;                      \
+            k_rollout_greedy<c, r><<<grid_for(n_env, TILE, 2), TILE, smem, st>>>(                        \
                 make_view<c, r>(state, n_env), env_offset, seed, piece_set, n_steps, wts, stats);        \
+        }                                                                                                \
         return check_launch("tb_rollout");                                                               \
     }
     TB_SHAPES(X)
