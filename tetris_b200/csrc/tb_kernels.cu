@@ -182,7 +182,7 @@ k_reset(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const ui
 // ---------------------------------------------------------------------------------------------
 // K1 afterstates.
 //
-// A CTA owns a tile of TILE = 256 envs.  Phase A (thread per env): load + transpose the board, build the env
+// A CTA owns a tile of TILE envs (= its thread count, a template parameter; 224 or 256).  Phase A (thread per env): load + transpose the board, build the env
 // record in shared memory, append the env to the list of its piece.  Phase B (warp per window): all lanes of a
 // warp work on envs holding the SAME piece -- lane = (env k of the window, anchor column c) -- and walk the piece's
 // orientations in a warp-uniform loop, so the orientation descriptor is uniform, every loop over the piece's
@@ -190,11 +190,9 @@ k_reset(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const ui
 // Placements that clear a line only need the general evaluation for their FEATURES (legality follows from the
 // full-row count); they go to a CTA-wide queue and are evaluated one thread per item in phase S.
 // ---------------------------------------------------------------------------------------------
-constexpr int TILE = 256;
-constexpr int NWARPS = TILE / 32;
 constexpr int QCAP = 512;
 
-template <int C, int R>
+template <int C, int R, int TILE>
 struct CtaSmem {
     using K = Env<C, R>;
     uint32_t rec[TILE * K::WORDS];
@@ -210,10 +208,10 @@ struct CtaSmem {
     uint32_t ori[32], piece[16];
 };
 // K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements
-struct BestSmem { unsigned long long best[TILE]; };
+template <int TILE> struct BestSmem { unsigned long long best[TILE]; };
 
-template <int C, int R>
-__device__ __forceinline__ void stage_cta(CtaSmem<C, R> &sm)
+template <int C, int R, int TILE>
+__device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
 {
     if (threadIdx.x < kNumOris) {
         sm.ori[threadIdx.x] = c_ori[threadIdx.x];
@@ -225,6 +223,21 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R> &sm)
     if (threadIdx.x < kNumPieces) sm.piece[threadIdx.x] = c_piece[threadIdx.x];
     for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = run_tab_entry<R>((uint32_t)m);
     __syncthreads();
+}
+
+// insert a zero above every one of the low 16 bits
+__device__ __forceinline__ uint32_t spread16(uint32_t x)
+{
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+// legal columns per orientation (16 bits each, orientation-major) -> loop-local slot bits c * n + o
+__device__ __forceinline__ uint32_t slots_of(uint32_t v, int n)
+{
+    return n == 2 ? (spread16(v & 0xFFFFu) | (spread16(v >> 16) << 1)) : (v & 0xFFFFu);
 }
 
 template <bool DIRS>
@@ -246,8 +259,8 @@ __device__ __forceinline__ float *feat_row(float *__restrict__ feats, int64_t en
 
 // Append `packed` of the flagged lanes to the CTA queue (one shared atomic per warp).  Returns false for a lane
 // whose item did not fit (the caller evaluates it in place).
-template <int C, int R>
-__device__ __forceinline__ bool queue_push(CtaSmem<C, R> &sm, bool flag, uint32_t packed, int lane)
+template <int C, int R, int TILE>
+__device__ __forceinline__ bool queue_push(CtaSmem<C, R, TILE> &sm, bool flag, uint32_t packed, int lane)
 {
     const unsigned bal = __ballot_sync(FULLMASK, flag);
     if (bal == 0u) return true;
@@ -273,14 +286,15 @@ __device__ __noinline__ void eval_slow_outofline(const uint32_t *col, uint32_t d
 // lane -> (env k of the window, column c); envs per window
 template <int C> struct Win { static constexpr int EPW = 32 / C; };
 
-template <int C, int R, bool DIRS, int MINB>
-__global__ void __launch_bounds__(TILE, MINB)
-k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
-              int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
+template <int C, int R, bool DIRS, int TILE>
+__device__ __forceinline__ void
+afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
+                 int *__restrict__ count_out, int a_stride, const F8 &dirs, int flags)
 {
     using K = Env<C, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaSmem<C, R> &sm = *reinterpret_cast<CtaSmem<C, R> *>(smem_raw);
+    constexpr int NWARPS = TILE / 32;
+    CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
     stage_cta(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool want_terminal = (flags & TB_FLAG_INCLUDE_TERMINAL) != 0;
@@ -307,9 +321,8 @@ k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__res
             constexpr int NC = C - W + 1, EPW = 32 / NC;
             const int k = lane / NC, c = lane - k * NC;
             const bool lane_ok = k < EPW;
-            const uint32_t segmask = lane_ok ? (((1u << NC) - 1u) << (k * NC)) : 0u;
             const int nwin = (np + EPW - 1) / EPW;
-            for (int win = (warp + p + 3 * l) & (NWARPS - 1); win < nwin; win += NWARPS) {
+            for (int win = (warp + p + 3 * l) % NWARPS; win < nwin; win += NWARPS) {
                 const int idx = win * EPW + k;
                 const bool on = lane_ok && idx < np;
                 const int env = on ? (int)sm.list[p][idx] : 0;
@@ -317,30 +330,28 @@ k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__res
                 Neigh<C, R, W> nb;
                 load_neigh<C, R, W>(rec, c, nb);
                 float *row = feat_row(feats, e0 + env, a_stride, sbase + c * n);
-                uint32_t vbits = 0u;
+                uint32_t vsel = 0u;                         // leader lane: legal columns of its env, 16 bits per orientation
 #pragma unroll 1
                 for (int o = 0; o < n; ++o) {
                     const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[ob + o]);
                     const int slot = sbase + c * n + o;
-                    bool slow = false;
+                    bool slow = false, legal = false;
                     if (on) {
                         Eval ev;
                         const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
                         if (status == kFastDone) emit_row<DIRS>(row + 8 * o, ev, dirs);
                         else if (status == kFastClears) slow = !ev.terminal || want_terminal;
                         else slow = want_terminal;
-                        if (!ev.terminal) vbits |= 1u << (c * n + o);
+                        legal = !ev.terminal;
                     }
+                    vsel |= ((__ballot_sync(FULLMASK, legal) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
                     if (!queue_push(sm, slow, (uint32_t)(env << 6 | slot), lane)) {
                         Eval e2;                            // queue full: evaluate in place
                         eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[ob + o], c, &e2);
                         emit_row<DIRS>(row + 8 * o, e2, dirs);
                     }
                 }
-                if (on) {
-                    const uint32_t v = __reduce_or_sync(segmask, vbits);
-                    if (c == 0) sm.vloc[env][l] = v;
-                }
+                if (on && c == 0) sm.vloc[env][l] = vsel;
             }
         };
 #pragma unroll 1
@@ -377,12 +388,30 @@ k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__res
         // ---- legal-action masks, thread per env (coalesced)
         if (e < sv.n_env) {
             const uint32_t pw = sm.piece[sm.pid[tid]];
-            const int s1 = (int)(pw & 3u) * (C - (int)((pw >> 2) & 7u) + 1);
-            const unsigned long long v = (unsigned long long)sm.vloc[tid][0] | ((unsigned long long)sm.vloc[tid][1] << s1);
+            const int n0 = (int)(pw & 3u), n1 = (int)((pw >> 5) & 3u);
+            const int s1 = n0 * (C - (int)((pw >> 2) & 7u) + 1);
+            const unsigned long long v = (unsigned long long)slots_of(sm.vloc[tid][0], n0) |
+                                         ((unsigned long long)slots_of(sm.vloc[tid][1], n1) << s1);
             if (valid_out) valid_out[e] = v;
             if (count_out) count_out[e] = __popcll(v);
         }
     }
+}
+
+template <int C, int R, bool DIRS, int TILE, int MINB>
+__global__ void __launch_bounds__(TILE, MINB)
+k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
+              int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
+{
+    afterstates_body<C, R, DIRS, TILE>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
+}
+// 224 threads x 3 CTAs per SM leaves 96 registers per thread (launch bounds alone make ptxas settle on 80)
+template <int C, int R, bool DIRS>
+__global__ void __maxnreg__(96)
+k_afterstates_224(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
+                  int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
+{
+    afterstates_body<C, R, DIRS, 224>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
 }
 
 // Afterstates with boards (compat layer / small batches): one thread per (env, slot), general path.
@@ -629,14 +658,15 @@ __device__ __forceinline__ unsigned long long score_key(uint32_t ord, int slot)
 // rebuilds the env record in shared memory every step.  Per step: A (thread per env) record + piece lists,
 // B (warp per window of same-piece envs) score every legal placement and keep the first arg-max per env,
 // S (thread per item) the line-clearing placements, C (thread per env) apply the chosen placement.
-template <int C, int R>
-__global__ void __launch_bounds__(TILE, 2)
+template <int C, int R, int TILE, int MINB>
+__global__ void __launch_bounds__(TILE, MINB)
 k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats)
 {
     using K = Env<C, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaSmem<C, R> &sm = *reinterpret_cast<CtaSmem<C, R> *>(smem_raw);
-    BestSmem &bs = *reinterpret_cast<BestSmem *>(smem_raw + ((sizeof(CtaSmem<C, R>) + 15) & ~(size_t)15));
+    constexpr int NWARPS = TILE / 32;
+    CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
+    BestSmem<TILE> &bs = *reinterpret_cast<BestSmem<TILE> *>(smem_raw + ((sizeof(CtaSmem<C, R, TILE>) + 15) & ~(size_t)15));
     __shared__ long long s_blk[TB_ST_COUNT];
     stage_cta(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -679,9 +709,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 constexpr int NC = C - W + 1, EPW = 32 / NC;
                 const int k = lane / NC, c = lane - k * NC;
                 const bool lane_ok = k < EPW;
-                const uint32_t segmask = lane_ok ? (((1u << NC) - 1u) << (k * NC)) : 0u;
                 const int nwin = (np + EPW - 1) / EPW;
-                for (int win = (warp + p + 3 * l) & (NWARPS - 1); win < nwin; win += NWARPS) {
+                for (int win = (warp + p + 3 * l) % NWARPS; win < nwin; win += NWARPS) {
                     const int idx = win * EPW + k;
                     const bool on = lane_ok && idx < np;
                     const int env = on ? (int)sm.list[p][idx] : 0;
@@ -711,12 +740,18 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                             atomicMax(&bs.best[env], score_key(orderable(fitness(e2.f, wts.v)), slot));
                         }
                     }
-                    if (on) {
-                        // first arg-max over the env's lanes: highest score, then lowest slot
-                        const uint32_t m = __reduce_max_sync(segmask, best_ord);
-                        const uint32_t sl = __reduce_min_sync(segmask, best_ord == m ? (uint32_t)best_slot : 255u);
-                        if (c == 0) { sm.vloc[env][l] = m; sm.bslot[env][l] = (uint8_t)sl; }
+                    // first arg-max over the env's NC lanes: highest score, then lowest slot (= lowest column, then o)
+                    uint32_t m = best_ord;
+#pragma unroll
+                    for (int d = 1; d < NC; d <<= 1) {
+                        const uint32_t m2 = __shfl_down_sync(FULLMASK, m, d);
+                        if (c + d < NC) m = max(m, m2);
                     }
+                    m = __shfl_sync(FULLMASK, m, k * NC);                      // the segment's maximum, from its leader
+                    const uint32_t hit = (__ballot_sync(FULLMASK, best_ord == m) >> (k * NC)) & ((1u << NC) - 1u);
+                    const int src = k * NC + __ffs((int)hit) - 1;              // lowest column that reaches it
+                    const int sl = __shfl_sync(FULLMASK, best_slot, src & 31);
+                    if (on && c == 0) { sm.vloc[env][l] = m; sm.bslot[env][l] = (uint8_t)sl; }
                 }
             };
 #pragma unroll 1
@@ -1045,17 +1080,22 @@ int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_
     if (a_stride < 1) return fail("%s: a_stride must be >= the piece set's slot count", __func__);
     cudaStream_t st = (cudaStream_t)stream;
     const F8 dirs = f8_from(directions, 1.0f);
-    const int minb = tuning_int("TB_K1_MINB", 3) == 2 ? 2 : 3;
+    const int cfg = tuning_int("TB_K1_CFG", 0);
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
-        const size_t smem = sizeof(CtaSmem<c, r>);                                                       \
-        const unsigned grid = grid_for(n_env, TILE, minb);                                               \
-        void (*kern)(StateView, float *, unsigned long long *, int *, int, F8, int) =                    \
-            directions ? (minb == 2 ? k_afterstates<c, r, true, 2> : k_afterstates<c, r, true, 3>)       \
-                       : (minb == 2 ? k_afterstates<c, r, false, 2> : k_afterstates<c, r, false, 3>);    \
+        typedef void (*kern_t)(StateView, float *, unsigned long long *, int *, int, F8, int);           \
+        kern_t kern; size_t smem; int tile, minb;                                                        \
+        if (cfg == 1) { tile = 224; minb = 3; smem = sizeof(CtaSmem<c, r, 224>);                         \
+            kern = directions ? k_afterstates_224<c, r, true> : k_afterstates_224<c, r, false>; }        \
+        else if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<c, r, 128>);                    \
+            kern = directions ? k_afterstates<c, r, true, 128, 5> : k_afterstates<c, r, false, 128, 5>; }\
+        else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<c, r, 256>);                    \
+            kern = directions ? k_afterstates<c, r, true, 256, 2> : k_afterstates<c, r, false, 256, 2>; }\
+        else { tile = 256; minb = 3; smem = sizeof(CtaSmem<c, r, 256>);                                  \
+            kern = directions ? k_afterstates<c, r, true, 256, 3> : k_afterstates<c, r, false, 256, 3>; }\
         if (opt_in_smem((const void *)kern, smem)) return -2;                                            \
-        kern<<<grid, TILE, smem, st>>>(make_view<c, r>(state, n_env), feats_out,                         \
-                                       (unsigned long long *)valid_out, count_out, a_stride, dirs, flags); \
+        kern<<<grid_for(n_env, tile, minb), tile, smem, st>>>(make_view<c, r>(state, n_env), feats_out,  \
+            (unsigned long long *)valid_out, count_out, a_stride, dirs, flags);                          \
         return check_launch("tb_afterstates");                                                           \
     }
     TB_SHAPES(X)
@@ -1119,9 +1159,17 @@ int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uin
             k_rollout_random<c, r><<<grid_for(n_env, 128, 8), 128, 0, st>>>(make_view<c, r>(state, n_env), \
                 env_offset, seed, piece_set, n_steps, stats);                                            \
         else {                                                                                           \
-            const size_t smem = ((sizeof(CtaSmem<c, r>) + 15) & ~(size_t)15) + sizeof(BestSmem);         \
-            if (opt_in_smem((const void *)k_rollout_greedy<c, r>, smem)) return -2;                      \
-            k_rollout_greedy<c, r><<<grid_for(n_env, TILE, 2), TILE, smem, st>>>(                        \
+            typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *);               \
+            kern_t kern; size_t smem; int tile, minb;                                                    \
+            const int k3cfg = tuning_int("TB_K3_CFG", 0);                                                \
+            if (k3cfg == 1) { tile = 160; minb = 3; kern = k_rollout_greedy<c, r, 160, 3>;               \
+                smem = ((sizeof(CtaSmem<c, r, 160>) + 15) & ~(size_t)15) + sizeof(BestSmem<160>); }      \
+            else if (k3cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<c, r, 128, 4>;          \
+                smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
+            else { tile = 256; minb = 2; kern = k_rollout_greedy<c, r, 256, 2>;                          \
+                smem = ((sizeof(CtaSmem<c, r, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }      \
+            if (opt_in_smem((const void *)kern, smem)) return -2;                                        \
+            kern<<<grid_for(n_env, tile, minb), tile, smem, st>>>(                                       \
                 make_view<c, r>(state, n_env), env_offset, seed, piece_set, n_steps, wts, stats);        \
         }                                                                                                \
         return check_launch("tb_rollout");                                                               \
