@@ -28,6 +28,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
     if (hmax <= R) build_env<C, R>(col, runtab, rec);      // the record's precondition: a non-terminal board
     const uint32_t pw = kPieceHost[piece];
     const int n = piece_num_slots(pw, C);
+    const unsigned long long vslots = hmax <= R ? valid_slots<C, R>(col, pw, kOriHost) : 0ull;
     for (int s = 0; s < n; ++s) {
         int ori, c;
         slot_to_placement(pw, C, s, ori, c);
@@ -56,6 +57,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
         for (int r = 0; r < S::N; ++r) rows_out[s * S::N + r] = (uint16_t)(wo[r >> 1] >> (16 * (r & 1)));
         // placement_valid (heights + full-row count only) must agree with the terminal flag
         if (hmax <= R && placement_valid<C, R>(col, d, c, hmax) != (full.terminal == 0)) return -1;
+        if (hmax <= R && (int)((vslots >> s) & 1ull) != (full.terminal == 0)) return -7;   // heights + near-full gate
     }
     return n;
 }

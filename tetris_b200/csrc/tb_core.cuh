@@ -794,6 +794,58 @@ TB_HD bool placement_valid(const uint32_t *col, uint32_t d, int c, int hmax)
     return top - popc32(full) <= R;
 }
 
+// Legal-slot mask of a piece on a board (game.py:69 over the enumeration of tetromino.py), one thread per env,
+// from column heights alone wherever that decides it: a placement whose top stays at or below row R is legal; one
+// that reaches above R is legal only if it clears enough rows, which needs a row that is full but for <= 4 cells
+// (`nearfull`, a bit-sliced count of the empty cells of every row) -- only then is the exact test run.
+// `ori` = the orientation table (shared memory on the device).  Precondition: every column height <= R.
+template <int C, int R>
+TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uint32_t *ori)
+{
+    using S = Shape<C, R>;
+    const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
+    const int total = n0 * (C - w0 + 1) + n1 * (C - w1 + 1);
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < C; ++k) any |= col[k];
+    const int hmax = height_of(any);
+    if (hmax + 4 <= R) return (1ull << total) - 1ull;   // every piece is at most 4 rows tall
+    uint64_t hp = 0;                                    // heights, 5 bits per column
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;            // bit-sliced count of empty cells per row
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        hp |= (uint64_t)height_of(col[k]) << (5 * k);
+        const uint32_t e = ~col[k] & S::ALL;
+        const uint32_t k0 = c0 & e; c0 ^= e;
+        const uint32_t k1 = c1 & k0; c1 ^= k0;
+        const uint32_t k2 = c2 & k1; c2 ^= k1;
+        c3 |= k2;
+    }
+    const uint32_t nearfull = ~(c3 | (c2 & (c1 | c0)));  // rows with at most 4 empty cells
+    unsigned long long m = 0ull;
+    for (int l = 0; l < 2; ++l) {
+        const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase;
+        const int sbase = l ? n0 * (C - w0 + 1) : 0;
+        for (int o = 0; o < n; ++o) {
+            const uint32_t d = ori[ob + o];
+            const int b0 = desc_bot(d, 0), b1 = desc_bot(d, 1), b2 = desc_bot(d, 2), b3 = desc_bot(d, 3);
+            const int ph = desc_ph(d);
+            const uint32_t chgm = mask_lo(desc_chg(d));
+            for (int c = 0; c + w <= C; ++c) {
+                const uint32_t hw = (uint32_t)(hp >> (5 * c));
+                int a = (int)(hw & 31u) - b0;
+                if (w > 1) a = imax(a, (int)((hw >> 5) & 31u) - b1);
+                if (w > 2) a = imax(a, (int)((hw >> 10) & 31u) - b2);
+                if (w > 3) a = imax(a, (int)((hw >> 15) & 31u) - b3);
+                bool ok = imax(hmax, a + ph) <= R;
+                if (!ok && ((nearfull >> a) & chgm) != 0u) ok = placement_valid<C, R>(col, d, c, hmax);
+                m |= (unsigned long long)ok << (sbase + c * n + o);
+            }
+        }
+    }
+    return m;
+}
+
 // State.__init__ on a caller-supplied board (state.py:5-38): clear the full rows among the `chg` changed lines
 // starting at row a, terminal test, features.  ppcr = pieces_per_changed_row packed 4 bits each.
 template <int C, int R>

@@ -116,39 +116,24 @@ __device__ __forceinline__ int max_height(const uint32_t *col)
     for (int c = 0; c < C; ++c) any |= col[c];
     return height_of(any);
 }
-// does the piece have at least one legal placement on this board?  (is_game_over, game.py:94-100)
-template <int C, int R>
-__device__ __forceinline__ bool any_valid(const uint32_t *col, uint32_t pw, const uint32_t *s_ori)
-{
-    const int hmax = max_height<C>(col);
-    if (hmax + 4 <= R) return true;                     // every piece is at most 4 rows tall
-    const int n = piece_num_slots(pw, C);
-    for (int s = 0; s < n; ++s) {
-        int ori, c;
-        slot_to_placement(pw, C, s, ori, c);
-        if (placement_valid<C, R>(col, s_ori[ori], c, hmax)) return true;
-    }
-    return false;
-}
-// mask of legal slots
+// mask of legal slots (game.py:69); 0 <=> the piece cannot be placed: game over (is_game_over, game.py:94-100)
 template <int C, int R>
 __device__ __forceinline__ unsigned long long valid_mask(const uint32_t *col, uint32_t pw, const uint32_t *s_ori)
 {
-    const int n = piece_num_slots(pw, C);
-    const int hmax = max_height<C>(col);
-    if (hmax + 4 <= R) return (1ull << n) - 1ull;
-    unsigned long long m = 0;
-    for (int s = 0; s < n; ++s) {
-        int ori, c;
-        slot_to_placement(pw, C, s, ori, c);
-        if (placement_valid<C, R>(col, s_ori[ori], c, hmax)) m |= 1ull << s;
-    }
-    return m;
+    return valid_slots<C, R>(col, pw, s_ori);
 }
+template <int C, int R>
+__device__ __forceinline__ bool any_valid(const uint32_t *col, uint32_t pw, const uint32_t *s_ori)
+{
+    return valid_slots<C, R>(col, pw, s_ori) != 0ull;
+}
+// position of the n-th (0-based) set bit of m; n < popc(m)
 __device__ __forceinline__ int nth_set_bit(unsigned long long m, int n)
 {
-    for (int i = 0; i < n; ++i) m &= m - 1ull;
-    return __ffsll((long long)m) - 1;
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    const int plo = __popc(lo);
+    const bool low = n < plo;
+    return (low ? 0 : 32) + (int)__fns(low ? lo : hi, 0u, (low ? n : n - plo) + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -582,10 +567,11 @@ __device__ __forceinline__ void stats_flush(const LaneStats &s, long long *s_blk
 }
 
 // Apply the chosen placement to the lane's env: lock, clear, reward, next piece, game-over, auto-reset.
+// Returns the legal-slot mask of the NEW piece on the NEW board (never 0: a finished env is reset in place).
 template <int C, int R>
-__device__ __forceinline__ void apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece_set,
-                                                uint64_t key, const uint32_t *s_ori, const uint32_t *s_piece,
-                                                LaneStats &st)
+__device__ __forceinline__ unsigned long long
+apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece_set, uint64_t key,
+                const uint32_t *s_ori, const uint32_t *s_piece, LaneStats &st)
 {
     int a, term;
     uint32_t full;
@@ -593,7 +579,8 @@ __device__ __forceinline__ void apply_placement(uint32_t *col, Meta &mt, uint2 &
     const int lc = popc32(full);
     int rew = lc - 1;
     mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
-    const bool dn = !any_valid<C, R>(col, s_piece[mt.piece], s_ori);
+    unsigned long long vm = valid_mask<C, R>(col, s_piece[mt.piece], s_ori);
+    const bool dn = vm == 0ull;
     if (dn) rew -= 100;
     ep.x += 1u; ep.y += (uint32_t)lc;
     st.placements += 1; st.lines += lc; st.reward += rew;
@@ -607,7 +594,9 @@ __device__ __forceinline__ void apply_placement(uint32_t *col, Meta &mt, uint2 &
         for (int k = 0; k < C; ++k) col[k] = 0u;
         mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
         ep = make_uint2(0u, 0u);
+        vm = (1ull << piece_num_slots(s_piece[mt.piece], C)) - 1ull;      // empty board: everything is legal
     }
+    return vm;
 }
 
 // random policy: everything is per-env, one thread per env, board in registers for all n_steps
@@ -626,16 +615,24 @@ k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
         Meta mt = unpack_meta(sv.meta[e]);
         uint2 ep = sv.epi[e];
         const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
+        unsigned long long vm = valid_mask<C, R>(col, s_piece[mt.piece], s_ori);
         for (int t = 0; t < n_steps; ++t) {
             const uint32_t pw = s_piece[mt.piece];
-            const unsigned long long vm = valid_mask<C, R>(col, pw, s_ori);
-            const int nv = __popcll(vm);
             st.afterstates += piece_num_slots(pw, C);
-            const int action = (int)bounded(rng32(key, mt.draws, 1u), (uint32_t)nv);
+            if (vm == 0ull) {
+                // no legal placement: only reachable from a caller-supplied dead state -> start a new episode
+#pragma unroll
+                for (int k = 0; k < C; ++k) col[k] = 0u;
+                mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
+                ep = make_uint2(0u, 0u);
+                vm = (1ull << piece_num_slots(s_piece[mt.piece], C)) - 1ull;
+                continue;
+            }
+            const int action = (int)bounded(rng32(key, mt.draws, 1u), (uint32_t)__popcll(vm));
             const int slot = nth_set_bit(vm, action);
             int ori, c;
             slot_to_placement(pw, C, slot, ori, c);
-            apply_placement<C, R>(col, mt, ep, s_ori[ori], c, piece_set, key, s_ori, s_piece, st);
+            vm = apply_placement<C, R>(col, mt, ep, s_ori[ori], c, piece_set, key, s_ori, s_piece, st);
         }
         store_board<C, R>(sv, e, col);
         sv.meta[e] = pack_meta<C>(col, mt);
