@@ -175,25 +175,28 @@ k_reset(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const ui
 // Placements that clear a line only need the general evaluation for their FEATURES (legality follows from the
 // full-row count); they go to a CTA-wide queue and are evaluated one thread per item in phase S.
 // ---------------------------------------------------------------------------------------------
-constexpr int QCAP = 512;
+constexpr int QWARP = 64;            // slow-path queue entries per warp
+constexpr int kNumJobs = 2 * kNumPieces;
 
 template <int C, int R, int TILE>
 struct CtaSmem {
     using K = Env<C, R>;
     uint32_t rec[TILE * K::WORDS];
     uint32_t odesc[kNumOris][kOriWords]; // orientation descriptors, decoded (OriU): broadcast 128-bit loads
-    uint32_t vloc[TILE][2];              // K1: legal placements of each env per column loop, loop-local bit c * n + o
+    uint32_t vloc[TILE][2];              // K1: legal placements of each env per column loop (16 bits per orientation)
                                          // K3: best orderable score of each env per column loop
-    uint16_t queue[QCAP];                // line-clearing placements: env << 6 | slot
+    uint16_t queue[TILE / 32][QWARP];    // per warp: line-clearing placements, env << 6 | slot
     uint16_t run[RunTab<R>::SIZE];
     uint8_t list[kNumPieces][TILE];      // tile-local env indices grouped by piece
     uint8_t pid[TILE];                   // piece of each env of the tile
     uint8_t bslot[TILE][2];              // K3: slot of the best score per column loop
-    int cnt[kNumPieces + 1];             // envs per piece; [kNumPieces] = queue length
+    int cnt[2][kNumPieces + 1];          // envs per piece, double-buffered by tile / step parity
+    uint32_t job[kNumJobs];              // (piece, column loop): p | l << 4 | w << 5 | n << 8 | ob << 10 | sbase << 16
     uint32_t ori[32], piece[16];
 };
-// K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements
-template <int TILE> struct BestSmem { unsigned long long best[TILE]; };
+// K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements,
+// and per-warp episode statistics
+template <int TILE> struct BestSmem { unsigned long long best[TILE]; long long wstat[TILE / 32][TB_ST_COUNT]; };
 
 template <int C, int R, int TILE>
 __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
@@ -206,8 +209,31 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
         sm.odesc[threadIdx.x][27] = 0u;
     }
     if (threadIdx.x < kNumPieces) sm.piece[threadIdx.x] = c_piece[threadIdx.x];
+    if (threadIdx.x < kNumJobs) {
+        const int p = threadIdx.x >> 1, l = threadIdx.x & 1;
+        const uint32_t pw = c_piece[p];
+        const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
+        const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase, sbase = l ? n0 * (C - w0 + 1) : 0;
+        sm.job[threadIdx.x] = (uint32_t)p | (uint32_t)l << 4 | (uint32_t)w << 5 | (uint32_t)(w <= C ? n : 0) << 8 |
+                              (uint32_t)ob << 10 | (uint32_t)sbase << 16;
+    }
+    if (threadIdx.x <= kNumPieces) { sm.cnt[0][threadIdx.x] = 0; sm.cnt[1][threadIdx.x] = 0; }
     for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = run_tab_entry<R>((uint32_t)m);
     __syncthreads();
+}
+
+// Append `packed` of the flagged lanes to the warp's queue.  Returns false for a lane whose item did not fit
+// (the caller evaluates it in place).  qn is warp-uniform.
+__device__ __forceinline__ bool queue_push(uint16_t *queue, int &qn, bool flag, uint32_t packed, int lane)
+{
+    const unsigned bal = __ballot_sync(FULLMASK, flag);
+    if (bal == 0u) return true;
+    const int pos = qn + __popc(bal & ((1u << lane) - 1u));
+    qn += __popc(bal);
+    if (!flag) return true;
+    if (pos >= QWARP) return false;
+    queue[pos] = (uint16_t)packed;
+    return true;
 }
 
 // insert a zero above every one of the low 16 bits
@@ -242,23 +268,6 @@ __device__ __forceinline__ float *feat_row(float *__restrict__ feats, int64_t en
     return feats + ((size_t)env * (size_t)a_stride + (size_t)slot) * 8;
 }
 
-// Append `packed` of the flagged lanes to the CTA queue (one shared atomic per warp).  Returns false for a lane
-// whose item did not fit (the caller evaluates it in place).
-template <int C, int R, int TILE>
-__device__ __forceinline__ bool queue_push(CtaSmem<C, R, TILE> &sm, bool flag, uint32_t packed, int lane)
-{
-    const unsigned bal = __ballot_sync(FULLMASK, flag);
-    if (bal == 0u) return true;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&sm.cnt[kNumPieces], __popc(bal));
-    base = __shfl_sync(FULLMASK, base, 0);
-    if (!flag) return true;
-    const int pos = base + __popc(bal & ((1u << lane) - 1u));
-    if (pos >= QCAP) return false;
-    sm.queue[pos] = (uint16_t)packed;
-    return true;
-}
-
 template <int V> struct IntC { static constexpr int value = V; };
 
 // general (from-scratch) evaluation kept out of line: it is the rare path and would otherwise be inlined per orientation
@@ -267,9 +276,6 @@ __device__ __noinline__ void eval_slow_outofline(const uint32_t *col, uint32_t d
 {
     eval_slow<C, R>(col, d, c, *ev, nullptr);
 }
-
-// lane -> (env k of the window, column c); envs per window
-template <int C> struct Win { static constexpr int EPW = 32 / C; };
 
 template <int C, int R, bool DIRS, int TILE>
 __device__ __forceinline__ void
@@ -284,28 +290,32 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool want_terminal = (flags & TB_FLAG_INCLUDE_TERMINAL) != 0;
     const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
+    uint16_t *queue = sm.queue[warp];
+    int par = 0;
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
         const int64_t e0 = tile * TILE, e = e0 + tid;
-        if (tid <= kNumPieces) sm.cnt[tid] = 0;
-        __syncthreads();                                   // also: the previous tile is done with rec / queue / vloc
-        // ---- phase A
+        int *cnt = sm.cnt[par];
+        // ---- phase A (thread per env).  cnt[par] was zeroed during the previous tile's phase B.
         sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
         if (e < sv.n_env) {
             uint32_t col[C];
             load_board<C, R>(sv, e, col);
             const Meta mt = unpack_meta(sv.meta[e]);
             build_env<C, R>(col, sm.run, sm.rec + tid * K::WORDS);
-            sm.list[mt.piece][atomicAdd(&sm.cnt[mt.piece], 1)] = (uint8_t)tid;
+            sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
             sm.pid[tid] = (uint8_t)mt.piece;
         }
         __syncthreads();
-        // ---- phase B: per piece, per column loop of the piece; a window = EPW envs x (C - W + 1) columns
-        auto column_loop = [&](auto wtag, int p, int np, int l, int n, int ob, int sbase) {
+        if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
+        // ---- phase B (warp per window): per (piece, column loop) job; a window = EPW envs x (C - W + 1) columns
+        int qn = 0;
+        auto column_loop = [&](auto wtag, uint32_t jb, int np) {
             constexpr int W = decltype(wtag)::value;
             constexpr int NC = C - W + 1, EPW = 32 / NC;
             const int k = lane / NC, c = lane - k * NC;
             const bool lane_ok = k < EPW;
+            const int p = jb & 15, l = (jb >> 4) & 1, n = (jb >> 8) & 3;
             const int nwin = (np + EPW - 1) / EPW;
             for (int win = (warp + p + 3 * l) % NWARPS; win < nwin; win += NWARPS) {
                 const int idx = win * EPW + k;
@@ -314,55 +324,47 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 const uint32_t *rec = sm.rec + env * K::WORDS;
                 Neigh<C, R, W> nb;
                 load_neigh<C, R, W>(rec, c, nb);
-                float *row = feat_row(feats, e0 + env, a_stride, sbase + c * n);
                 uint32_t vsel = 0u;                         // leader lane: legal columns of its env, 16 bits per orientation
 #pragma unroll 1
                 for (int o = 0; o < n; ++o) {
-                    const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[ob + o]);
-                    const int slot = sbase + c * n + o;
+                    const int oi = (int)((jb >> 10) & 63u) + o;
+                    const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[oi]);
+                    const int slot = (int)(jb >> 16) + c * n + o;
                     bool slow = false, legal = false;
                     if (on) {
                         Eval ev;
                         const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
-                        if (status == kFastDone) emit_row<DIRS>(row + 8 * o, ev, dirs);
+                        if (status == kFastDone) emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs);
                         else if (status == kFastClears) slow = !ev.terminal || want_terminal;
                         else slow = want_terminal;
                         legal = !ev.terminal;
                     }
                     vsel |= ((__ballot_sync(FULLMASK, legal) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
-                    if (!queue_push(sm, slow, (uint32_t)(env << 6 | slot), lane)) {
+                    if (!queue_push(queue, qn, slow, (uint32_t)(env << 6 | slot), lane)) {
                         Eval e2;                            // queue full: evaluate in place
-                        eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[ob + o], c, &e2);
-                        emit_row<DIRS>(row + 8 * o, e2, dirs);
+                        eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[oi], c, &e2);
+                        emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), e2, dirs);
                     }
                 }
                 if (on && c == 0) sm.vloc[env][l] = vsel;
             }
         };
 #pragma unroll 1
-        for (int p = 0; p < kNumPieces; ++p) {
-            const int np = sm.cnt[p];
-            if (np == 0) continue;
-            const uint32_t pw = sm.piece[p];
-            const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
-#pragma unroll 1
-            for (int l = 0; l < 2; ++l) {
-                const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase;
-                const int sbase = l ? n0 * (C - w0 + 1) : 0;
-                if (n == 0) break;
-                switch (w) {
-                case 1: column_loop(IntC<1>(), p, np, l, n, ob, sbase); break;
-                case 2: column_loop(IntC<2>(), p, np, l, n, ob, sbase); break;
-                case 3: column_loop(IntC<3>(), p, np, l, n, ob, sbase); break;
-                default: if (C >= 4) column_loop(IntC<4>(), p, np, l, n, ob, sbase); break;
-                }
+        for (int j = 0; j < kNumJobs; ++j) {
+            const uint32_t jb = sm.job[j];
+            const int np = cnt[jb & 15];
+            if (np == 0 || ((jb >> 8) & 3u) == 0u) continue;
+            switch ((jb >> 5) & 7u) {
+            case 1: column_loop(IntC<1>(), jb, np); break;
+            case 2: column_loop(IntC<2>(), jb, np); break;
+            case 3: column_loop(IntC<3>(), jb, np); break;
+            default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np); break;
             }
         }
-        __syncthreads();
-        // ---- phase S: line-clearing placements, one thread per item, general evaluation
-        const int qn = min(sm.cnt[kNumPieces], QCAP);
-        for (int i = tid; i < qn; i += TILE) {
-            const uint32_t packed = sm.queue[i];
+        // ---- phase S: this warp's line-clearing placements, one lane per item, general evaluation
+        __syncwarp();
+        for (int i = lane; i < min(qn, QWARP); i += 32) {
+            const uint32_t packed = queue[i];
             const int env = (int)(packed >> 6), slot = (int)(packed & 63u);
             int ori, cc;
             slot_to_placement(sm.piece[sm.pid[env]], C, slot, ori, cc);
@@ -370,6 +372,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[ori], cc, ev, nullptr);
             emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs);
         }
+        __syncthreads();                                   // every warp is done with rec / list; vloc is complete
         // ---- legal-action masks, thread per env (coalesced)
         if (e < sv.n_env) {
             const uint32_t pw = sm.piece[sm.pid[tid]];
@@ -651,10 +654,11 @@ __device__ __forceinline__ unsigned long long score_key(uint32_t ord, int slot)
     return ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)slot);   // ties: lower slot
 }
 
-// Greedy linear policy.  Same tile scheme as K1; a thread keeps its env's board in registers for all n_steps and
-// rebuilds the env record in shared memory every step.  Per step: A (thread per env) record + piece lists,
-// B (warp per window of same-piece envs) score every legal placement and keep the first arg-max per env,
-// S (thread per item) the line-clearing placements, C (thread per env) apply the chosen placement.
+// Greedy linear policy.  Same tile scheme as K1; thread tid owns env tid of the tile for all n_steps.  Per step:
+// A (thread per env) env record + piece lists, B (warp per window of same-piece envs) score every legal placement and
+// keep the first arg-max per env and column loop, S (per warp) its line-clearing placements, C (thread per env) apply
+// the chosen placement.  Between steps the board lives in the record's column words, not in registers: only the
+// bag / counters stay in registers across phase B.  Episode statistics are aggregated per warp in shared memory.
 template <int C, int R, int TILE, int MINB>
 __global__ void __launch_bounds__(TILE, MINB)
 k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats)
@@ -664,48 +668,58 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
     constexpr int NWARPS = TILE / 32;
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
     BestSmem<TILE> &bs = *reinterpret_cast<BestSmem<TILE> *>(smem_raw + ((sizeof(CtaSmem<C, R, TILE>) + 15) & ~(size_t)15));
-    __shared__ long long s_blk[TB_ST_COUNT];
     stage_cta(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
-    LaneStats st;
-    stats_zero(st);
+    uint16_t *queue = sm.queue[warp];
+    long long *wstat = bs.wstat[warp];
+    if (lane < TB_ST_COUNT) wstat[lane] = 0;
+    int par = 0;
+    uint32_t *myrec = sm.rec + tid * K::WORDS;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t e = tile * TILE + tid;
         const bool active = e < sv.n_env;
-        uint32_t col[C];
         Meta mt; mt.piece = 0; mt.bag = 0u; mt.draws = 0u;
         uint2 ep = make_uint2(0u, 0u);
-        uint64_t key = 0;
-        if (active) {
-            load_board<C, R>(sv, e, col);
-            mt = unpack_meta(sv.meta[e]);
-            ep = sv.epi[e];
-            key = env_key(seed, (uint64_t)(env_offset + e));
-        } else {
+        {
+            uint32_t col[C];
+            if (active) {
+                load_board<C, R>(sv, e, col);
+                mt = unpack_meta(sv.meta[e]);
+                ep = sv.epi[e];
+            } else {
 #pragma unroll
-            for (int i = 0; i < C; ++i) col[i] = 0u;
+                for (int i = 0; i < C; ++i) col[i] = 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
         }
-        for (int t = 0; t < n_steps; ++t) {
-            if (tid <= kNumPieces) sm.cnt[tid] = 0;
-            __syncthreads();                               // phase C / S of the previous step are done with smem
-            // ---- phase A
+        for (int t = 0; t < n_steps; ++t, par ^= 1) {
+            int *cnt = sm.cnt[par];
+            // ---- phase A (thread per env).  cnt[par] was zeroed during the previous step's phase B.
             sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
             bs.best[tid] = 0ull;
+            int n_slots = 0;
             if (active) {
-                build_env<C, R>(col, sm.run, sm.rec + tid * K::WORDS);
-                sm.list[mt.piece][atomicAdd(&sm.cnt[mt.piece], 1)] = (uint8_t)tid;
+                uint32_t col[C];
+#pragma unroll
+                for (int i = 0; i < C; ++i) col[i] = myrec[K::COLX + 2 + i];
+                build_env<C, R>(col, sm.run, myrec);
+                sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
                 sm.pid[tid] = (uint8_t)mt.piece;
-                st.afterstates += piece_num_slots(sm.piece[mt.piece], C);
+                n_slots = piece_num_slots(sm.piece[mt.piece], C);
             }
             __syncthreads();
+            if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
             // ---- phase B: score every legal placement, keep the first arg-max per env and column loop
-            auto column_loop = [&](auto wtag, int p, int np, int l, int n, int ob, int sbase) {
+            int qn = 0;
+            auto column_loop = [&](auto wtag, uint32_t jb, int np) {
                 constexpr int W = decltype(wtag)::value;
                 constexpr int NC = C - W + 1, EPW = 32 / NC;
                 const int k = lane / NC, c = lane - k * NC;
                 const bool lane_ok = k < EPW;
+                const int p = jb & 15, l = (jb >> 4) & 1, n = (jb >> 8) & 3;
                 const int nwin = (np + EPW - 1) / EPW;
                 for (int win = (warp + p + 3 * l) % NWARPS; win < nwin; win += NWARPS) {
                     const int idx = win * EPW + k;
@@ -718,8 +732,9 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     int best_slot = 0;
 #pragma unroll 1
                     for (int o = 0; o < n; ++o) {
-                        const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[ob + o]);
-                        const int slot = sbase + c * n + o;
+                        const int oi = (int)((jb >> 10) & 63u) + o;
+                        const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[oi]);
+                        const int slot = (int)(jb >> 16) + c * n + o;
                         bool slow = false;
                         if (on) {
                             Eval ev;
@@ -731,9 +746,9 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                                 slow = !ev.terminal;
                             }
                         }
-                        if (!queue_push(sm, slow, (uint32_t)(env << 6 | slot), lane)) {
+                        if (!queue_push(queue, qn, slow, (uint32_t)(env << 6 | slot), lane)) {
                             Eval e2;                        // queue full: evaluate in place
-                            eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[ob + o], c, &e2);
+                            eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[oi], c, &e2);
                             atomicMax(&bs.best[env], score_key(orderable(fitness(e2.f, wts.v)), slot));
                         }
                     }
@@ -752,29 +767,21 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 }
             };
 #pragma unroll 1
-            for (int p = 0; p < kNumPieces; ++p) {
-                const int np = sm.cnt[p];
-                if (np == 0) continue;
-                const uint32_t pw = sm.piece[p];
-                const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
-#pragma unroll 1
-                for (int l = 0; l < 2; ++l) {
-                    const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase;
-                    const int sbase = l ? n0 * (C - w0 + 1) : 0;
-                    if (n == 0) break;
-                    switch (w) {
-                    case 1: column_loop(IntC<1>(), p, np, l, n, ob, sbase); break;
-                    case 2: column_loop(IntC<2>(), p, np, l, n, ob, sbase); break;
-                    case 3: column_loop(IntC<3>(), p, np, l, n, ob, sbase); break;
-                    default: if (C >= 4) column_loop(IntC<4>(), p, np, l, n, ob, sbase); break;
-                    }
+            for (int j = 0; j < kNumJobs; ++j) {
+                const uint32_t jb = sm.job[j];
+                const int np = cnt[jb & 15];
+                if (np == 0 || ((jb >> 8) & 3u) == 0u) continue;
+                switch ((jb >> 5) & 7u) {
+                case 1: column_loop(IntC<1>(), jb, np); break;
+                case 2: column_loop(IntC<2>(), jb, np); break;
+                case 3: column_loop(IntC<3>(), jb, np); break;
+                default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np); break;
                 }
             }
-            __syncthreads();
-            // ---- phase S
-            const int qn = min(sm.cnt[kNumPieces], QCAP);
-            for (int i = tid; i < qn; i += TILE) {
-                const uint32_t packed = sm.queue[i];
+            // ---- phase S: this warp's line-clearing placements
+            __syncwarp();
+            for (int i = lane; i < min(qn, QWARP); i += 32) {
+                const uint32_t packed = queue[i];
                 const int env = (int)(packed >> 6), slot = (int)(packed & 63u);
                 int ori, cc;
                 slot_to_placement(sm.piece[sm.pid[env]], C, slot, ori, cc);
@@ -783,8 +790,15 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 atomicMax(&bs.best[env], score_key(orderable(fitness(ev.f, wts.v)), slot));
             }
             __syncthreads();
-            // ---- phase C
+            // ---- phase C (thread per env): apply the choice, draw the next piece, game over / auto-reset
+            int lc = 0;
+            bool placed = false, dn = false;
+            uint2 ep_done = make_uint2(0u, 0u);
             if (active) {
+                uint32_t col[C];
+#pragma unroll
+                for (int i = 0; i < C; ++i) col[i] = myrec[K::COLX + 2 + i];
+                const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
                 unsigned long long best = bs.best[tid];
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
@@ -796,25 +810,72 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 }
                 if (best != 0ull) {
                     const int slot = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
-                    int ori, cc;
+                    int ori, cc, a, term;
+                    uint32_t full;
                     slot_to_placement(sm.piece[mt.piece], C, slot, ori, cc);
-                    apply_placement<C, R>(col, mt, ep, sm.ori[ori], cc, piece_set, key, sm.ori, sm.piece, st);
-                } else {
-                    // no legal placement: only reachable from a caller-supplied dead state -> start a new episode
+                    place_and_clear<C, R>(col, sm.ori[ori], cc, a, full, term);
+                    lc = popc32(full);
+                    placed = true;
+                    mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
+                    dn = !any_valid<C, R>(col, sm.piece[mt.piece], sm.ori);
+                    ep.x += 1u; ep.y += (uint32_t)lc;
+                    ep_done = ep;
+                }
+                if (dn || !placed) {
+                    // game over (or a caller-supplied dead state): start a new episode in place
 #pragma unroll
                     for (int i = 0; i < C; ++i) col[i] = 0u;
                     mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
                     ep = make_uint2(0u, 0u);
                 }
+#pragma unroll
+                for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
+            }
+            // episode statistics of the step, aggregated over the warp (ballots are warp-uniform; lane 0 accumulates)
+            {
+                const unsigned bp = __ballot_sync(FULLMASK, placed), bd = __ballot_sync(FULLMASK, dn);
+                const unsigned b1 = __ballot_sync(FULLMASK, lc == 1), b2 = __ballot_sync(FULLMASK, lc == 2);
+                const unsigned b3 = __ballot_sync(FULLMASK, lc == 3), b4 = __ballot_sync(FULLMASK, lc == 4);
+                const int n_after = __reduce_add_sync(FULLMASK, n_slots);
+                long long se = 0, sl = 0, me = 0, ml = 0;
+                if (bd) {
+                    se = warp_sum(dn ? (long long)ep_done.x : 0ll); sl = warp_sum(dn ? (long long)ep_done.y : 0ll);
+                    me = warp_max(dn ? (long long)ep_done.x : 0ll); ml = warp_max(dn ? (long long)ep_done.y : 0ll);
+                }
+                if (lane == 0) {
+                    const int np_ = __popc(bp), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3), n4 = __popc(b4);
+                    const int nd = __popc(bd), nl = n1 + 2 * n2 + 3 * n3 + 4 * n4;
+                    wstat[TB_ST_PLACEMENTS] += np_; wstat[TB_ST_EPISODES] += nd; wstat[TB_ST_LINES] += nl;
+                    wstat[TB_ST_REWARD] += nl - np_ - 100 * nd; wstat[TB_ST_AFTERSTATES] += n_after;
+                    wstat[TB_ST_LINES0] += np_ - n1 - n2 - n3 - n4; wstat[TB_ST_LINES1] += n1; wstat[TB_ST_LINES2] += n2;
+                    wstat[TB_ST_LINES3] += n3; wstat[TB_ST_LINES4] += n4;
+                    if (bd) {
+                        wstat[TB_ST_SUM_EP_STEPS] += se; wstat[TB_ST_SUM_EP_LINES] += sl;
+                        if (me > wstat[TB_ST_MAX_EP_STEPS]) wstat[TB_ST_MAX_EP_STEPS] = me;
+                        if (ml > wstat[TB_ST_MAX_EP_LINES]) wstat[TB_ST_MAX_EP_LINES] = ml;
+                    }
+                }
             }
         }
+        __syncthreads();                                   // nobody reads this thread's record any more
         if (active) {
+            uint32_t col[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i) col[i] = myrec[K::COLX + 2 + i];
             store_board<C, R>(sv, e, col);
             sv.meta[e] = pack_meta<C>(col, mt);
             sv.epi[e] = ep;
         }
     }
-    stats_flush(st, s_blk, stats);
+    // per-warp statistics -> global
+    __syncwarp();
+    if (lane < TB_ST_COUNT) {
+        const long long r = wstat[lane];
+        if (r != 0) {
+            if (lane == TB_ST_MAX_EP_LINES || lane == TB_ST_MAX_EP_STEPS) atomicMax((long long *)&stats[lane], r);
+            else atomicAdd((unsigned long long *)&stats[lane], (unsigned long long)r);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1159,8 +1220,10 @@ int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uin
             typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *);               \
             kern_t kern; size_t smem; int tile, minb;                                                    \
             const int k3cfg = tuning_int("TB_K3_CFG", 0);                                                \
-            if (k3cfg == 1) { tile = 160; minb = 3; kern = k_rollout_greedy<c, r, 160, 3>;               \
-                smem = ((sizeof(CtaSmem<c, r, 160>) + 15) & ~(size_t)15) + sizeof(BestSmem<160>); }      \
+            if (k3cfg == 1) { tile = 256; minb = 3; kern = k_rollout_greedy<c, r, 256, 3>;               \
+                smem = ((sizeof(CtaSmem<c, r, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }      \
+            else if (k3cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<c, r, 128, 5>;          \
+                smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
             else if (k3cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<c, r, 128, 4>;          \
                 smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
             else { tile = 256; minb = 2; kern = k_rollout_greedy<c, r, 256, 2>;                          \
