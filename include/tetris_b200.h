@@ -146,6 +146,22 @@ int tb_rollout(void *state, int num_columns, int num_rows, int64_t n_env, int64_
                int piece_set, int n_steps, int policy, const float *weights, int64_t *stats, void *stream);
 
 /*
+ * Tetris.perform_rollouts / single_rollout (game.py:129-160) for every env and every action at once.  For each legal
+ * enumeration slot s of env e and each of n_forks forks: take the action, draw the next piece, then follow the
+ * in-kernel policy for `length - 1` more placements; the fork's return is -1 if the game ended on the way
+ * (game.py:134,143-145), else the sum of the follow-up rewards (lines - 1 each, game.py:86,141).
+ *   child_state caller-owned scratch of tb_state_bytes(C, R, n_env * a_stride * n_forks) bytes; child
+ *               d = (e * a_stride + s) * n_forks + f draws pieces from the stream (seed2, child_offset + d), starting
+ *               from the parent's bag (the reference forks share one global sampler and are not reproducible)
+ *   ret_sum     int32[n_env][a_stride]: sum of the forks' returns (mean = ret_sum / n_forks); 0 for illegal slots
+ *   valid_out   nullable uint64[n_env]: legal slots
+ *   stats       int64[TB_ST_COUNT] device: statistics of the follow-up placements are added (as tb_rollout)
+ */
+int tb_rollout_values(const void *state, int num_columns, int num_rows, int64_t n_env, int piece_set, void *child_state,
+                      int a_stride, int n_forks, int length, int policy, const float *weights, uint64_t seed2,
+                      int64_t child_offset, int32_t *ret_sum, uint64_t *valid_out, int64_t *stats, void *stream);
+
+/*
  * State interchange (state.py:22-25,162-172; utils.py:179-191 needs the board on the host).
  * export: rows_out uint16[count][R+4], heights_out uint8[count][C], piece_out uint8[count] (all nullable)
  * import: rows_in  uint16[count][R+4] (heights are recomputed), piece_in nullable uint8[count]

@@ -679,6 +679,67 @@ void orc_batch_rollout_mt(orc_batch *b, int T, int policy, const float *weights,
     free(jobs); free(th);
 }
 
+/* Tetris.perform_rollouts / single_rollout (game.py:129-160) for every env and every action, with the fork RNG
+ * convention of tb_rollout_values: child d = (e * a_stride + slot) * n_forks + f is a one-env copy of the parent
+ * whose pieces come from the stream (seed2, child_offset + d), continuing the parent's bag.  ret_sum[e][slot] = sum
+ * over forks of the rollout return: -1 if the game ended (after the action or on the way), else the sum of the
+ * follow-up rewards.  valid[e] = legal slots. */
+void orc_batch_rollout_values(orc_batch *b, int a_stride, int n_forks, int length, int policy, const float *weights,
+                              uint64_t seed2, int64_t child_offset, int32_t *ret_sum, uint64_t *valid)
+{
+    const int C = b->C, R = b->R, N = R + 4;
+    orc_batch *t = orc_batch_new(C, R, b->piece_set, 1, 0, seed2);
+    for (int64_t e = 0; e < b->n_env; ++e) {
+        orc_state st[ORC_MAX_A];
+        int h[ORC_MAX_C];
+        for (int c = 0; c < C; ++c) h[c] = b->h[e * C + c];
+        const int n = enumerate(C, R, b->piece[e], b->rep + (size_t)e * N * C, h, st, 0);
+        uint64_t vm = 0;
+        for (int s = 0; s < a_stride; ++s) {
+            int sum = 0;
+            const int legal = s < n && !st[s].terminal;
+            if (legal) vm |= 1ull << s;
+            for (int f = 0; legal && f < n_forks; ++f) {
+                t->env_offset = child_offset + ((int64_t)e * a_stride + s) * n_forks + f;
+                memcpy(t->rep, b->rep + (size_t)e * N * C, (size_t)(N * C));
+                memcpy(t->h, b->h + (size_t)e * C, sizeof(int32_t) * (size_t)C);
+                t->piece[0] = b->piece[e]; t->bag[0] = b->bag[e]; t->draws[0] = b->draws[e];
+                t->ep_steps[0] = 0; t->ep_lines[0] = 0;
+                uint8_t dn = 0; int32_t rew = 0, lc = 0;
+                env_step(t, 0, s, 1, NULL, 0, NULL, &rew, &dn, &lc);               /* game.py:132 */
+                int ret = 0;
+                if (dn) ret = -1;                                                   /* :133-137 */
+                for (int k = 0; !dn && k < length - 1; ++k) {                       /* :139-145 */
+                    orc_state s2[ORC_MAX_A];
+                    int h2[ORC_MAX_C];
+                    for (int c = 0; c < C; ++c) h2[c] = t->h[c];
+                    const int n2 = enumerate(C, R, t->piece[0], t->rep, h2, s2, policy == 1);
+                    int nv = 0, action = 0;
+                    for (int i = 0; i < n2; ++i) nv += !s2[i].terminal;
+                    if (policy == 0) {
+                        action = (int)bounded(orc_rng(t->seed, (uint64_t)t->env_offset, t->draws[0], 1u), (uint32_t)nv);
+                    } else {
+                        float best = 0.f; int kk = 0, have = 0;
+                        for (int i = 0; i < n2; ++i) {
+                            if (s2[i].terminal) continue;
+                            const float fv = fitness_w(s2[i].feat, weights);
+                            if (!have || fv > best) { best = fv; action = kk; have = 1; }
+                            ++kk;
+                        }
+                    }
+                    env_step(t, 0, action, 0, NULL, 0, NULL, &rew, &dn, &lc);
+                    ret += rew;
+                    if (dn) ret = -1;
+                }
+                sum += ret;
+            }
+            ret_sum[e * a_stride + s] = sum;
+        }
+        if (valid) valid[e] = vm;
+    }
+    orc_batch_free(t);
+}
+
 void orc_batch_rollout(orc_batch *b, int T, int policy, const float *weights, int64_t *stats /*[ST_COUNT]*/)
 {
     orc_batch_rollout_mt(b, T, policy, weights, stats, 1);

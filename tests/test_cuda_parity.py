@@ -306,3 +306,34 @@ def test_eval_states():
             assert np.array_equal(h_o[i].cpu().numpy(), o["heights"])
             assert np.array_equal(rows_o[i].cpu().numpy().view(np.uint16), rep_to_rows(o["rep"]))
             assert int(info[i, 0]) == o["n_cleared"] and bool(info[i, 2]) == o["terminal"]
+
+
+@pytest.mark.parametrize("policy", ["greedy", "random"])
+@pytest.mark.parametrize("shape", [(10, 20), (10, 10), (6, 12)])
+def test_rollout_values_vs_oracle(shape, policy):
+    """Tetris.perform_rollouts (game.py:129-160) for every env x action on the device -- forks, follow-up
+    policy steps, -1 on game over -- against the oracle's loop with the same fork RNG convention.  Bit-exact sums."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    Cc, R = shape
+    n, seed = 300, 21
+    env = BatchedTetris(Cc, R, n, piece_set=1, seed=seed, env_offset=3)
+    ob = orc.Batch(Cc, R, n, piece_set=1, seed=seed, env_offset=3)
+    ob.reset()
+    T0 = 14 if shape == (10, 20) else 9
+    env.rollout(T0, "random"); ob.rollout(T0, 0)          # boards tall enough that some forks end
+    _compare_state(env, ob)
+    before = (env.rows().copy(), env.piece.copy())
+    length, forks = 4, 3
+    mean, valid = env.rollout_values(length=length, n=forks, policy=policy, seed=1234)
+    want, wvalid = ob.rollout_values(length, forks, 0 if policy == "random" else 1, seed2=1234,
+                                     child_offset=3 * env.a_max * forks)
+    assert np.array_equal(valid.cpu().numpy().view(np.uint64), wvalid)
+    got = np.rint(mean.cpu().numpy() * forks).astype(np.int64)
+    assert np.array_equal(got, want)
+    assert (want < 0).any() and (want.min() >= -forks * max(1, length - 1))
+    assert np.array_equal(env.rows(), before[0]) and np.array_equal(env.piece, before[1])   # the envs are not stepped
+    # length 1: only the action itself -> 0, or -1 where the next piece cannot be placed (game.py:133-137)
+    m1, _ = env.rollout_values(length=1, n=2, policy=policy, seed=5)
+    w1, _ = ob.rollout_values(1, 2, 0, seed2=5, child_offset=3 * env.a_max * 2)
+    assert np.array_equal(np.rint(m1.cpu().numpy() * 2).astype(np.int64), w1)

@@ -139,6 +139,31 @@ class BatchedTetris:
                                              pol, w.ctypes.data_as(C.c_void_p), _ptr(self.stats), self._stream()))
         return self.stats
 
+    def rollout_values(self, length=5, n=5, policy="greedy", weights=None, seed=None):
+        """Tetris.perform_rollouts (game.py:150-160) for every env and every legal action at once, on the device.
+
+        Every (env, action) is forked n times: the action is applied, the next piece drawn from the fork's own
+        stream, and the in-kernel policy followed for length - 1 more placements.  Returns (mean return float64
+        [n_env, a_max] -- -1 for a fork that ended, else lines minus placements of the follow-up steps, 0 where the
+        slot is not a legal action --, valid int64[n_env] bit mask of legal slots).  The envs themselves are not
+        stepped.  Follow-up statistics are added to self.stats.
+        """
+        pol = {"random": _lib.POLICY_RANDOM, "greedy": _lib.POLICY_GREEDY, 0: 0, 1: 1}[policy]
+        w = np.ascontiguousarray(BCTS_WEIGHTS if weights is None else weights, dtype=np.float32)
+        seed2 = (self.seed ^ 0xF02C) if seed is None else int(seed) & (2 ** 64 - 1)
+        L = _lib.lib()
+        n_child = self.n_env * self.a_max * int(n)
+        with torch.cuda.device(self.device):
+            child = torch.empty(L.tb_state_bytes(self.num_columns, self.num_rows, n_child), dtype=torch.uint8,
+                                device=self.device)
+            ret = torch.empty((self.n_env, self.a_max), dtype=torch.int32, device=self.device)
+            valid = torch.empty(self.n_env, dtype=torch.int64, device=self.device)
+            _lib.check(L.tb_rollout_values(*self._common(), self.piece_set, _ptr(child), self.a_max, int(n), int(length),
+                                           pol, w.ctypes.data_as(C.c_void_p), seed2,
+                                           self.env_offset * self.a_max * int(n), _ptr(ret), _ptr(valid),
+                                           _ptr(self.stats), self._stream()))
+        return ret.double() / float(n), valid
+
     def stats_dict(self, stats=None):
         s = (self.stats if stats is None else stats).cpu().tolist()
         return dict(zip(_lib.STATS, s))

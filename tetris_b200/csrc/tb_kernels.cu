@@ -57,6 +57,9 @@ static StateView make_view(const void *base, int64_t n_env)
 // device helpers
 // ---------------------------------------------------------------------------------------------
 struct Meta { int piece; uint32_t bag, draws; };
+// piece byte of an env that takes no further part in a no-reset rollout (tb_rollout_values forks)
+constexpr int kPieceDead = 0xFF;      // game over: its rollout return is -1 (game.py:138-145)
+constexpr int kPieceVoid = 0xFE;      // fork of an illegal / non-existent action
 
 __device__ __forceinline__ Meta unpack_meta(uint4 m)
 {
@@ -574,7 +577,7 @@ __device__ __forceinline__ void stats_flush(const LaneStats &s, long long *s_blk
 template <int C, int R>
 __device__ __forceinline__ unsigned long long
 apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece_set, uint64_t key,
-                const uint32_t *s_ori, const uint32_t *s_piece, LaneStats &st)
+                const uint32_t *s_ori, const uint32_t *s_piece, LaneStats &st, bool no_reset = false)
 {
     int a, term;
     uint32_t full;
@@ -593,6 +596,7 @@ apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece
         st.sum_ep_steps += ep.x; st.sum_ep_lines += ep.y;
         st.max_ep_lines = imax(st.max_ep_lines, (int)ep.y);
         st.max_ep_steps = imax(st.max_ep_steps, (int)ep.x);
+        if (no_reset) { mt.piece = kPieceDead; return 0ull; }             // the env stays finished (rollout forks)
 #pragma unroll
         for (int k = 0; k < C; ++k) col[k] = 0u;
         mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
@@ -605,7 +609,8 @@ apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece
 // random policy: everything is per-env, one thread per env, board in registers for all n_steps
 template <int C, int R>
 __global__ void __launch_bounds__(128)
-k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, int64_t *stats)
+k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, int64_t *stats,
+                 int no_reset)
 {
     __shared__ uint32_t s_ori[32], s_piece[16];
     __shared__ long long s_blk[TB_ST_COUNT];
@@ -616,13 +621,16 @@ k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
         uint32_t col[C];
         load_board<C, R>(sv, e, col);
         Meta mt = unpack_meta(sv.meta[e]);
+        if (mt.piece >= kNumPieces) continue;              // finished / void fork: untouched
         uint2 ep = sv.epi[e];
         const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
         unsigned long long vm = valid_mask<C, R>(col, s_piece[mt.piece], s_ori);
         for (int t = 0; t < n_steps; ++t) {
+            if (mt.piece >= kNumPieces) break;
             const uint32_t pw = s_piece[mt.piece];
             st.afterstates += piece_num_slots(pw, C);
             if (vm == 0ull) {
+                if (no_reset) { mt.piece = kPieceDead; break; }
                 // no legal placement: only reachable from a caller-supplied dead state -> start a new episode
 #pragma unroll
                 for (int k = 0; k < C; ++k) col[k] = 0u;
@@ -635,7 +643,7 @@ k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             const int slot = nth_set_bit(vm, action);
             int ori, c;
             slot_to_placement(pw, C, slot, ori, c);
-            vm = apply_placement<C, R>(col, mt, ep, s_ori[ori], c, piece_set, key, s_ori, s_piece, st);
+            vm = apply_placement<C, R>(col, mt, ep, s_ori[ori], c, piece_set, key, s_ori, s_piece, st, no_reset != 0);
         }
         store_board<C, R>(sv, e, col);
         sv.meta[e] = pack_meta<C>(col, mt);
@@ -661,7 +669,8 @@ __device__ __forceinline__ unsigned long long score_key(uint32_t ord, int slot)
 // bag / counters stay in registers across phase B.  Episode statistics are aggregated per warp in shared memory.
 template <int C, int R, int TILE, int MINB>
 __global__ void __launch_bounds__(TILE, MINB)
-k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats)
+k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats,
+                 int no_reset)
 {
     using K = Env<C, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -679,15 +688,17 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t e = tile * TILE + tid;
-        const bool active = e < sv.n_env;
+        const bool in_range = e < sv.n_env;
+        bool active = in_range;                            // false once finished in a no-reset rollout
         Meta mt; mt.piece = 0; mt.bag = 0u; mt.draws = 0u;
         uint2 ep = make_uint2(0u, 0u);
         {
             uint32_t col[C];
-            if (active) {
+            if (in_range) {
                 load_board<C, R>(sv, e, col);
                 mt = unpack_meta(sv.meta[e]);
                 ep = sv.epi[e];
+                active = mt.piece < kNumPieces;
             } else {
 #pragma unroll
                 for (int i = 0; i < C; ++i) col[i] = 0u;
@@ -821,7 +832,10 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     ep.x += 1u; ep.y += (uint32_t)lc;
                     ep_done = ep;
                 }
-                if (dn || !placed) {
+                if ((dn || !placed) && no_reset) {
+                    mt.piece = kPieceDead;                  // stays finished (rollout forks)
+                    active = false;
+                } else if (dn || !placed) {
                     // game over (or a caller-supplied dead state): start a new episode in place
 #pragma unroll
                     for (int i = 0; i < C; ++i) col[i] = 0u;
@@ -858,7 +872,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             }
         }
         __syncthreads();                                   // nobody reads this thread's record any more
-        if (active) {
+        if (in_range && (active || mt.piece == kPieceDead)) {
             uint32_t col[C];
 #pragma unroll
             for (int i = 0; i < C; ++i) col[i] = myrec[K::COLX + 2 + i];
@@ -876,6 +890,77 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             else atomicAdd((unsigned long long *)&stats[lane], (unsigned long long)r);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rollout forks (Tetris.single_rollout / perform_rollouts, game.py:129-160, for every env and every action).
+// Child d = (env * a_stride + slot) * n_forks + fork starts from the parent's board with `slot` applied, the
+// parent's bag, and its own RNG stream (seed2, child id); the next piece is drawn and tested for game over.
+// ---------------------------------------------------------------------------------------------
+template <int C, int R>
+__global__ void __launch_bounds__(128)
+k_fork(StateView parent, StateView child, int a_stride, int n_forks, uint64_t seed2, int64_t child_offset, int piece_set)
+{
+    __shared__ uint32_t s_ori[32], s_piece[16];
+    stage_tables(s_ori, s_piece);
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= child.n_env) return;
+    const int64_t e = d / ((int64_t)a_stride * n_forks);
+    const int slot = (int)((d / n_forks) % a_stride);
+    uint32_t col[C];
+    load_board<C, R>(parent, e, col);
+    Meta mt = unpack_meta(parent.meta[e]);
+    bool ok = mt.piece < kNumPieces;
+    int ori = 0, c = 0;
+    if (ok) {
+        const uint32_t pw = s_piece[mt.piece];
+        ok = slot < piece_num_slots(pw, C);
+        if (ok) {
+            slot_to_placement(pw, C, slot, ori, c);
+            ok = placement_valid<C, R>(col, s_ori[ori], c, max_height<C>(col));
+        }
+    }
+    if (!ok) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) col[k] = 0u;
+        mt.piece = kPieceVoid;
+    } else {
+        int a, term;
+        uint32_t full;
+        place_and_clear<C, R>(col, s_ori[ori], c, a, full, term);          // self.step(action): game.py:83
+        const uint64_t key = env_key(seed2, (uint64_t)(child_offset + d));
+        mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));   // :87
+        if (!any_valid<C, R>(col, s_piece[mt.piece], s_ori)) mt.piece = kPieceDead;              // :88, :133-137
+    }
+    store_board<C, R>(child, d, col);
+    child.meta[d] = pack_meta<C>(col, mt);
+    child.epi[d] = make_uint2(0u, 0u);
+}
+
+// Sum of the rollout returns of an (env, action)'s forks: -1 for a fork that ended (game.py:134,143-145), else the
+// lines cleared minus the placements made after the first step (reward = lines - 1 per step, game.py:86,141).
+__global__ void k_fork_returns(const uint4 *__restrict__ meta, const uint2 *__restrict__ epi, int64_t n_parent,
+                               int a_stride, int n_forks, int32_t *__restrict__ ret_sum,
+                               unsigned long long *__restrict__ valid)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_parent) return;
+    unsigned long long vm = 0ull;
+    for (int s = 0; s < a_stride; ++s) {
+        int sum = 0;
+        bool legal = false;
+        for (int f = 0; f < n_forks; ++f) {
+            const int64_t d = (e * a_stride + s) * n_forks + f;
+            const int piece = (int)((meta[d].z >> 16) & 0xffu);
+            if (piece == kPieceVoid) continue;
+            legal = true;
+            const uint2 ep = epi[d];
+            sum += piece == kPieceDead ? -1 : (int)ep.y - (int)ep.x;
+        }
+        ret_sum[e * a_stride + s] = sum;
+        if (legal && s < 64) vm |= 1ull << s;
+    }
+    if (valid) valid[e] = vm;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1200,8 +1285,8 @@ int tb_step(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64
     return -1;
 }
 
-int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
-               int n_steps, int policy, const float *weights, int64_t *stats, void *stream)
+static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
+                        int n_steps, int policy, const float *weights, int64_t *stats, void *stream, int no_reset)
 {
     TB_CHECK_COMMON();
     if (!stats) return fail("%s: stats is required", __func__);
@@ -1215,9 +1300,9 @@ int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uin
     if (C == c && R == r) {                                                                              \
         if (policy == TB_POLICY_RANDOM)                                                                  \
             k_rollout_random<c, r><<<grid_for(n_env, 128, 8), 128, 0, st>>>(make_view<c, r>(state, n_env), \
-                env_offset, seed, piece_set, n_steps, stats);                                            \
+                env_offset, seed, piece_set, n_steps, stats, no_reset);                                  \
         else {                                                                                           \
-            typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *);               \
+            typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int);          \
             kern_t kern; size_t smem; int tile, minb;                                                    \
             const int k3cfg = tuning_int("TB_K3_CFG", 0);                                                \
             if (k3cfg == 1) { tile = 256; minb = 3; kern = k_rollout_greedy<c, r, 256, 3>;               \
@@ -1230,9 +1315,45 @@ int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uin
                 smem = ((sizeof(CtaSmem<c, r, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }      \
             if (opt_in_smem((const void *)kern, smem)) return -2;                                        \
             kern<<<grid_for(n_env, tile, minb), tile, smem, st>>>(                                       \
-                make_view<c, r>(state, n_env), env_offset, seed, piece_set, n_steps, wts, stats);        \
+                make_view<c, r>(state, n_env), env_offset, seed, piece_set, n_steps, wts, stats, no_reset); \
         }                                                                                                \
         return check_launch("tb_rollout");                                                               \
+    }
+    TB_SHAPES(X)
+#undef X
+    return -1;
+}
+
+int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
+               int n_steps, int policy, const float *weights, int64_t *stats, void *stream)
+{
+    return rollout_impl(state, C, R, n_env, env_offset, seed, piece_set, n_steps, policy, weights, stats, stream, 0);
+}
+
+int tb_rollout_values(const void *state, int C, int R, int64_t n_env, int piece_set, void *child_state, int a_stride,
+                      int n_forks, int length, int policy, const float *weights, uint64_t seed2, int64_t child_offset,
+                      int32_t *ret_sum, uint64_t *valid_out, int64_t *stats, void *stream)
+{
+    TB_CHECK_COMMON();
+    if (!child_state || !ret_sum || !stats) return fail("%s: child_state, ret_sum and stats are required", __func__);
+    if (a_stride < 1 || a_stride > 64 || n_forks < 1 || length < 1) return fail("%s: bad a_stride / n_forks / length", __func__);
+    if (piece_set < 0 || piece_set > 1) return fail("%s: piece_set must be 0 or 1", __func__);
+    const int64_t n_child = n_env * a_stride * n_forks;
+    cudaStream_t st = (cudaStream_t)stream;
+#define X(c, r)                                                                                          \
+    if (C == c && R == r) {                                                                              \
+        k_fork<c, r><<<(unsigned)((n_child + 127) / 128), 128, 0, st>>>(make_view<c, r>(state, n_env),   \
+            make_view<c, r>(child_state, n_child), a_stride, n_forks, seed2, child_offset, piece_set);   \
+        if (check_launch("tb_rollout_values(fork)")) return -2;                                          \
+        if (length > 1) {                                                                                \
+            const int rc = rollout_impl(child_state, c, r, n_child, child_offset, seed2, piece_set, length - 1, policy, \
+                                        weights, stats, stream, 1);                                      \
+            if (rc) return rc;                                                                           \
+        }                                                                                                \
+        const StateView cv = make_view<c, r>(child_state, n_child);                                      \
+        k_fork_returns<<<(unsigned)((n_env + 127) / 128), 128, 0, st>>>(cv.meta, cv.epi, n_env, a_stride, n_forks, \
+            ret_sum, (unsigned long long *)valid_out);                                                   \
+        return check_launch("tb_rollout_values(reduce)");                                                \
     }
     TB_SHAPES(X)
 #undef X
