@@ -189,6 +189,19 @@ int tb_eval_states(int num_columns, int num_rows, int64_t n, const uint16_t *row
  */
 int tb_fitness(int64_t n, const float *feats, const float *weights, float *out, void *stream);
 
+/*
+ * Softmax policy over every env's legal afterstates and the policy-gradient term of a chosen action
+ * (utils.py:26-38: compute_action_probabilities, grad_of_log_action_probabilities), float64 like the reference.
+ *   feats     float32[n_env][a_stride][8] as written by tb_afterstates (16-byte aligned), valid uint64[n_env]
+ *   weights   HOST double[8]; utilities = feats . weights / temperature, shifted by their maximum before exp
+ *   actions   nullable int32[n_env]: chosen action as an enumeration slot (needed for grad_out)
+ *   probs_out nullable double[n_env][a_stride]: probability per slot, 0 for illegal slots
+ *   grad_out  nullable double[n_env][8]: feats[action] - sum_s probs[s] * feats[s]
+ */
+int tb_action_probabilities(int64_t n_env, int a_stride, const float *feats, const uint64_t *valid,
+                            const double *weights, double temperature, const int32_t *actions, double *probs_out,
+                            double *grad_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

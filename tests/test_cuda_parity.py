@@ -337,3 +337,31 @@ def test_rollout_values_vs_oracle(shape, policy):
     m1, _ = env.rollout_values(length=1, n=2, policy=policy, seed=5)
     w1, _ = ob.rollout_values(1, 2, 0, seed2=5, child_offset=3 * env.a_max * 2)
     assert np.array_equal(np.rint(m1.cpu().numpy() * 2).astype(np.int64), w1)
+
+
+def test_action_probabilities_vs_numpy():
+    """utils.compute_action_probabilities / grad_of_log_action_probabilities (utils.py:26-38) batched on
+    the device, against the reference's NumPy formulas per env.  float64; tolerance 1e-12 absolute on probabilities
+    (exp implementations differ in the last ulp), 1e-10 on the gradient."""
+    torch = _torch()
+    from tetris_b200 import BatchedTetris, utils
+    n = 2000
+    env = BatchedTetris(10, 20, n, piece_set=1, seed=8)
+    env.rollout(25, "random")
+    feats, valid, count = env.get_after_states()
+    w = np.array([-2.4, -1.9, -1.3, -1.2, -1.0, -0.9, 0.6, -0.1])
+    vm = valid.cpu().numpy().view(np.uint64)
+    bits = ((vm[:, None] >> np.arange(env.a_max, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    rng = np.random.default_rng(0)
+    slots = np.array([rng.choice(np.nonzero(b)[0]) for b in bits], np.int32)
+    for temp in (1.0, 0.25, 7.5):
+        probs, grad = env.action_probabilities(feats, valid, w, temperature=temp, actions=torch.as_tensor(slots))
+        probs, grad, f = probs.cpu().numpy(), grad.cpu().numpy(), feats.cpu().numpy()
+        assert not probs[~bits].any()
+        for e in range(0, n, 7):
+            fe = f[e][bits[e]].astype(np.float64)
+            want = utils.compute_action_probabilities(fe, w, temp)
+            assert np.allclose(probs[e][bits[e]], want, rtol=0, atol=1e-12), (e, temp)
+            k = int(np.nonzero(np.nonzero(bits[e])[0] == slots[e])[0][0])
+            assert np.allclose(grad[e], utils.grad_of_log_action_probabilities(fe, want, k), rtol=0, atol=1e-10)
+        assert np.allclose(probs.sum(axis=1), 1.0, atol=1e-12)

@@ -85,6 +85,8 @@ def lib():
     L.tb_eval_states.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
     L.tb_rollout_values.restype = i32
     L.tb_rollout_values.argtypes = [vp, i32, i32, i64, i32, vp, i32, i32, i32, i32, vp, u64, i64, vp, vp, vp, vp]
+    L.tb_action_probabilities.restype = i32
+    L.tb_action_probabilities.argtypes = [i64, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp]
     L.tb_slot_info.restype = i32
     L.tb_slot_info.argtypes = [i32, i32, i32, vp]
     L.tb_fitness.restype = i32
@@ -95,7 +97,7 @@ def lib():
 
 EXPORTS = ("tb_version", "tb_last_error", "tb_supported_shape", "tb_state_bytes", "tb_num_slots", "tb_a_max",
            "tb_reset", "tb_afterstates", "tb_afterstates_export", "tb_step", "tb_rollout", "tb_export_boards",
-           "tb_import_boards", "tb_eval_states", "tb_slot_info", "tb_fitness", "tb_rollout_values")
+           "tb_import_boards", "tb_eval_states", "tb_slot_info", "tb_fitness", "tb_rollout_values", "tb_action_probabilities")
 
 
 def check(rc):

@@ -164,6 +164,24 @@ class BatchedTetris:
                                            _ptr(self.stats), self._stream()))
         return ret.double() / float(n), valid
 
+    def action_probabilities(self, feats, valid, weights, temperature=1.0, actions=None):
+        """utils.compute_action_probabilities (utils.py:26-31) for every env over its legal afterstates, and -- when
+        `actions` (enumeration slots, int32[n_env]) is given -- utils.grad_of_log_action_probabilities
+        (utils.py:35-38).  float64 on the device.  Returns probs float64[n_env, a_max] (0 for illegal slots), or
+        (probs, grad float64[n_env, 8])."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert w.shape == (8,) and feats.shape == (self.n_env, self.a_max, 8) and feats.dtype == torch.float32
+        probs = torch.empty((self.n_env, self.a_max), dtype=torch.float64, device=self.device)
+        grad = a = None
+        if actions is not None:
+            a = actions.to(device=self.device, dtype=torch.int32).contiguous()
+            grad = torch.empty((self.n_env, 8), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_action_probabilities(self.n_env, self.a_max, _ptr(feats.contiguous()), _ptr(valid),
+                                                          w.ctypes.data_as(C.c_void_p), float(temperature), _ptr(a),
+                                                          _ptr(probs), _ptr(grad), self._stream()))
+        return probs if actions is None else (probs, grad)
+
     def stats_dict(self, stats=None):
         s = (self.stats if stats is None else stats).cpu().tolist()
         return dict(zip(_lib.STATS, s))

@@ -1070,6 +1070,52 @@ __global__ void k_fitness(int64_t n, const float *__restrict__ feats, F8 wts, fl
     out[i] = fitness(f, wts.v);
 }
 
+// Softmax policy over the legal afterstates of every env (utils.py:26-31 compute_action_probabilities) and the
+// gradient of the log-probability of the chosen action (utils.py:35-38), float64 like the reference's NumPy.
+// One thread per env; utilities are recomputed instead of stored (A <= 36 rows of 8 floats, L1/L2 resident).
+struct D8 { double v[8]; };
+__device__ __forceinline__ double utility(const float *__restrict__ row, const D8 &w, double inv_t)
+{
+    const float4 a = reinterpret_cast<const float4 *>(row)[0], b = reinterpret_cast<const float4 *>(row)[1];
+    double u = (double)a.x * w.v[0];
+    u += (double)a.y * w.v[1]; u += (double)a.z * w.v[2]; u += (double)a.w * w.v[3];
+    u += (double)b.x * w.v[4]; u += (double)b.y * w.v[5]; u += (double)b.z * w.v[6]; u += (double)b.w * w.v[7];
+    return u * inv_t;
+}
+__global__ void k_action_probs(int64_t n, int a_stride, const float *__restrict__ feats,
+                               const unsigned long long *__restrict__ valid, D8 w, double inv_t,
+                               const int32_t *__restrict__ actions, double *__restrict__ probs, double *__restrict__ grad)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const unsigned long long vm = valid[e];
+    const float *base = feats + (size_t)e * a_stride * 8;
+    double umax = -1.0e300;
+    for (unsigned long long m = vm; m; m &= m - 1) umax = fmax(umax, utility(base + 8 * (__ffsll((long long)m) - 1), w, inv_t));
+    double z = 0.0;
+    for (unsigned long long m = vm; m; m &= m - 1) z += exp(utility(base + 8 * (__ffsll((long long)m) - 1), w, inv_t) - umax);
+    const double inv_z = vm ? 1.0 / z : 0.0;
+    double mean[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < a_stride; ++s) {
+        double p = 0.0;
+        if (s < 64 && ((vm >> s) & 1ull)) {
+            const float *row = base + 8 * s;
+            p = exp(utility(row, w, inv_t) - umax) * inv_z;
+            if (grad) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mean[i] += p * (double)row[i];
+            }
+        }
+        if (probs) probs[(size_t)e * a_stride + s] = p;
+    }
+    if (grad) {
+        const int sel = actions ? actions[e] : -1;            // enumeration slot of the chosen action
+        const bool ok = sel >= 0 && sel < a_stride && sel < 64 && ((vm >> sel) & 1ull);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) grad[e * 8 + i] = ok ? (double)base[8 * sel + i] - mean[i] : 0.0;
+    }
+}
+
 }  // namespace tb
 
 // =============================================================================================
@@ -1422,6 +1468,22 @@ int tb_fitness(int64_t n, const float *feats, const float *weights, float *out, 
     if ((reinterpret_cast<uintptr_t>(feats) & 15u) != 0) return fail("%s: feats must be 16-byte aligned", __func__);
     k_fitness<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, feats, f8_from(weights, 0.0f), out);
     return check_launch("tb_fitness");
+}
+
+int tb_action_probabilities(int64_t n_env, int a_stride, const float *feats, const uint64_t *valid,
+                            const double *weights, double temperature, const int32_t *actions, double *probs_out,
+                            double *grad_out, void *stream)
+{
+    if (n_env <= 0) return fail("%s: n_env must be positive", __func__);
+    if (!feats || !valid || !weights) return fail("%s: feats, valid and weights are required", __func__);
+    if (a_stride < 1 || a_stride > 64) return fail("%s: a_stride must be in 1..64", __func__);
+    if (!(temperature > 0.0)) return fail("%s: temperature must be positive", __func__);
+    if ((reinterpret_cast<uintptr_t>(feats) & 15u) != 0) return fail("%s: feats must be 16-byte aligned", __func__);
+    D8 w;
+    for (int i = 0; i < 8; ++i) w.v[i] = weights[i];
+    k_action_probs<<<(unsigned)((n_env + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        n_env, a_stride, feats, (const unsigned long long *)valid, w, 1.0 / temperature, actions, probs_out, grad_out);
+    return check_launch("tb_action_probabilities");
 }
 
 }  // extern "C"
