@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-C, R, PIECE_SET = 10, 20, 1
+C, R, PIECE_SET = 10, 20, 1     # --board overrides C x R (BASELINE configs[4]: 10x20, 10x10, 6x12)
 STATE_READ_BYTES = 64          # 3 x 128-bit row planes + 128-bit meta per env (include/tetris_b200.h)
 METRIC = "placements/sec (env steps/sec), greedy-linear policy, whole job"
 
@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--rollout-steps", type=int, default=32, help="placements per env per step")
     ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--board", default="10x20", help="columns x rows: 10x20 (headline), 10x10, 6x12, 8x16")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu baseline / e2e side measurements")
     return ap.parse_args()
 
@@ -43,9 +44,9 @@ def parse():
 def config_of(args, n_gpus):
     return {
         "workload": "BASELINE configs[3] per-GPU shard: greedy linear policy (BCTS weights, game.py:111-118) playing "
-                    "with game-over + auto-reset, 10x20 board, 7-piece set; %d envs/GPU x %d placements per step"
-                    % (args.envs, args.rollout_steps),
-        "board": "10x20", "piece_set": "7-piece (game.py:41-47)", "policy": "greedy-linear BCTS",
+                    "with game-over + auto-reset, %dx%d board, 7-piece set; %d envs/GPU x %d placements per step"
+                    % (C, R, args.envs, args.rollout_steps),
+        "board": "%dx%d" % (C, R), "piece_set": "7-piece (game.py:41-47)", "policy": "greedy-linear BCTS",
         "envs_per_gpu": args.envs, "total_envs": args.envs * n_gpus, "rollout_steps": args.rollout_steps,
         "l2": "flushed between timed steps (256 MiB write outside the timed events)",
         "parallelism": "envs sharded over %d GPU(s); stats all-reduce only" % n_gpus,
@@ -128,7 +129,7 @@ def cpu_port_rate(seconds_target, threads, policy=1, seed=1):
     t0 = time.perf_counter()
     st = b.rollout(T, policy, threads=threads)
     dt = time.perf_counter() - t0
-    sample = "%d envs x %d placements (greedy BCTS, 10x20, 7-piece) in %.1f s on %d threads" % (n_env, T, dt, threads)
+    sample = "%d envs x %d placements (greedy BCTS, %dx%d, 7-piece) in %.1f s on %d threads" % (n_env, T, C, R, dt, threads)
     return n_env * T / dt, float(st[4]) / dt, sample
 
 
@@ -272,7 +273,7 @@ def run_ours(args):
         except Exception:
             pass
         out["roofline"] = {
-            "kernel": "k_afterstates<10,20> (K1: enumerate + 8 features for every placement of 2^20 envs)",
+            "kernel": "k_afterstates<%d,%d> (K1: enumerate + 8 features for every placement of %d envs)" % (C, R, E),
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": (prof.get("dram_bytes_read", 0) + prof.get("dram_bytes_write", 0)) or None,
             "traffic_source": "ncu --set full capture %s (profiles/), dram__bytes_read+write per launch on the "
@@ -367,6 +368,8 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    C, R = (int(x) for x in a.board.lower().split("x"))
+    STATE_READ_BYTES = 16 * ((R + 4 + 7) // 8 + 1)
     if a.impl == "reference":
         run_reference(a)
     else:
