@@ -62,11 +62,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.lo = self.hi = None
+
+    def mark_begin(self):
+        self.lo = len(self.lines)
+
+    def mark_end(self):
+        self.hi = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -87,7 +94,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        lines = self.lines[self.lo:self.hi] if self.lo is not None and self.hi is not None and self.hi > self.lo \
+            else self.lines[(self.lo or 0):]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -199,15 +208,16 @@ def run_ours(args):
             return reduce_stats(env.stats)                   # end-of-rollout reduction of episode statistics (NCCL)
         return env.stats
 
+    sampler = ClockSampler(local)
+    sampler.start()                                          # nvidia-smi takes a moment to start: begin before warm-up
     for _ in range(W):
         step()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sampler = ClockSampler(local)
-    sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark_begin()                                     # only samples taken during the timed region count
     wall0 = time.perf_counter()
     for s, e in ev:
         flush.zero_()
@@ -218,6 +228,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = sum(s.elapsed_time(e) for s, e in ev)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -311,10 +322,11 @@ def run_ours(args):
             hc = torch.empty(nl, dtype=torch.int32).pin_memory()
             ha = torch.zeros(nl, dtype=torch.int32).pin_memory()
             ho = torch.empty((nl, 8), dtype=torch.float32).pin_memory()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
             n_it = 3
-            for _ in range(n_it):
+            for it in range(n_it + 1):                                 # first iteration = warm-up (pinned pages, caches)
+                if it == 1:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
                 f, v, c = env2.get_after_states()
                 hf.copy_(f, non_blocking=True); hc.copy_(c, non_blocking=True)
                 torch.cuda.synchronize()

@@ -1,4 +1,5 @@
-"""Small fixed workload for ncu: every kernel of the hot path, twice (first launch = warm-up).
+"""Small fixed workload for ncu: every kernel of the hot path, twice (first launch = warm-up).  The rollouts run on
+boards after random play (tall, many terminal placements), K1 / K2 on boards after greedy play (as in bench.py).
 
     python profiles/prof_run.py [n_env] [rollout_steps]
 """
@@ -19,6 +20,7 @@ for _ in range(2):
     env.rollout(T, "greedy")
 for _ in range(2):
     env.rollout(T, "random")
+env.rollout(64, "greedy")          # back to greedy-play boards: K1 / K2 below see what bench.py's roofline leg sees
 feats = valid = count = None
 for _ in range(2):
     feats, valid, count = env.get_after_states()
