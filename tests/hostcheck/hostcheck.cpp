@@ -29,6 +29,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
     const uint32_t pw = kPieceHost[piece];
     const int n = piece_num_slots(pw, C);
     const unsigned long long vslots = hmax <= R ? valid_slots<C, R>(col, pw, kOriHost) : 0ull;
+    if (hmax <= R && (valid_slots<C, R, true>(col, pw, kOriHost) != 0ull) != (vslots != 0ull)) return -9;
     for (int s = 0; s < n; ++s) {
         int ori, c;
         slot_to_placement(pw, C, s, ori, c);

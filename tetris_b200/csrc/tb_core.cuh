@@ -799,7 +799,8 @@ TB_HD bool placement_valid(const uint32_t *col, uint32_t d, int c, int hmax)
 // that reaches above R is legal only if it clears enough rows, which needs a row that is full but for <= 4 cells
 // (`nearfull`, a bit-sliced count of the empty cells of every row) -- only then is the exact test run.
 // `ori` = the orientation table (shared memory on the device).  Precondition: every column height <= R.
-template <int C, int R>
+// ANY_ONLY: return non-zero as soon as one legal slot is found (the mask is then not complete).
+template <int C, int R, bool ANY_ONLY = false>
 TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uint32_t *ori)
 {
     using S = Shape<C, R>;
@@ -839,6 +840,7 @@ TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uin
                 if (w > 3) a = imax(a, (int)((hw >> 15) & 31u) - b3);
                 bool ok = imax(hmax, a + ph) <= R;
                 if (!ok && ((nearfull >> a) & chgm) != 0u) ok = placement_valid<C, R>(col, d, c, hmax);
+                if (ANY_ONLY && ok) return 1ull;        // is_game_over only asks whether a legal placement exists
                 m |= (unsigned long long)ok << (sbase + c * n + o);
             }
         }

@@ -128,7 +128,7 @@ __device__ __forceinline__ unsigned long long valid_mask(const uint32_t *col, ui
 template <int C, int R>
 __device__ __forceinline__ bool any_valid(const uint32_t *col, uint32_t pw, const uint32_t *s_ori)
 {
-    return valid_slots<C, R>(col, pw, s_ori) != 0ull;
+    return valid_slots<C, R, true>(col, pw, s_ori) != 0ull;
 }
 // position of the n-th (0-based) set bit of m; n < popc(m)
 __device__ __forceinline__ int nth_set_bit(unsigned long long m, int n)
@@ -396,15 +396,6 @@ k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__res
 {
     afterstates_body<C, R, DIRS, TILE>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
 }
-// 224 threads x 3 CTAs per SM leaves 96 registers per thread (launch bounds alone make ptxas settle on 80)
-template <int C, int R, bool DIRS>
-__global__ void __maxnreg__(96)
-k_afterstates_224(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
-                  int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
-{
-    afterstates_body<C, R, DIRS, 224>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
-}
-
 // Afterstates with boards (compat layer / small batches): one thread per (env, slot), general path.
 template <int C, int R>
 __global__ void __launch_bounds__(128)
@@ -1152,7 +1143,9 @@ static int sm_count()
     }
     return cached > 0 ? cached : 148;
 }
-// tuning knobs read from the environment (experiments only; the defaults are what ships)
+// Tuning knobs read from the environment (experiments only; the defaults are what ships and what is tested):
+//   TB_K1_CFG  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5
+//   TB_K3_CFG  0: 256 x 2 (default)   2: 128 x 4   3: 128 x 5
 static int tuning_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -1274,9 +1267,7 @@ int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_
     if (C == c && R == r) {                                                                              \
         typedef void (*kern_t)(StateView, float *, unsigned long long *, int *, int, F8, int);           \
         kern_t kern; size_t smem; int tile, minb;                                                        \
-        if (cfg == 1) { tile = 224; minb = 3; smem = sizeof(CtaSmem<c, r, 224>);                         \
-            kern = directions ? k_afterstates_224<c, r, true> : k_afterstates_224<c, r, false>; }        \
-        else if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<c, r, 128>);                    \
+        if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<c, r, 128>);                    \
             kern = directions ? k_afterstates<c, r, true, 128, 5> : k_afterstates<c, r, false, 128, 5>; }\
         else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<c, r, 256>);                    \
             kern = directions ? k_afterstates<c, r, true, 256, 2> : k_afterstates<c, r, false, 256, 2>; }\
@@ -1351,9 +1342,7 @@ static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_of
             typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int);          \
             kern_t kern; size_t smem; int tile, minb;                                                    \
             const int k3cfg = tuning_int("TB_K3_CFG", 0);                                                \
-            if (k3cfg == 1) { tile = 256; minb = 3; kern = k_rollout_greedy<c, r, 256, 3>;               \
-                smem = ((sizeof(CtaSmem<c, r, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }      \
-            else if (k3cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<c, r, 128, 5>;          \
+            if (k3cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<c, r, 128, 5>;          \
                 smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
             else if (k3cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<c, r, 128, 4>;          \
                 smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
