@@ -365,3 +365,31 @@ def test_action_probabilities_vs_numpy():
             k = int(np.nonzero(np.nonzero(bits[e])[0] == slots[e])[0][0])
             assert np.allclose(grad[e], utils.grad_of_log_action_probabilities(fe, want, k), rtol=0, atol=1e-10)
         assert np.allclose(probs.sum(axis=1), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 700])
+def test_ragged_sizes(n):
+    """Env counts around the warp / CTA-tile boundaries (tile = 256 envs): K1, K2, K3 against the oracle, with feature
+    directions and include_terminal, on a small board where game overs and line clears are frequent."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    dirs = np.array([-1, -1, -1, -1, -1, -1, 1, -1], np.float32)
+    for (Cc, R, ps) in ((6, 12, 1), (10, 10, 0)):
+        env = BatchedTetris(Cc, R, n, piece_set=ps, seed=n, feature_directions=dirs)
+        ob = orc.Batch(Cc, R, n, piece_set=ps, seed=n)
+        ob.reset()
+        for rnd in range(3):
+            env.rollout(7, "greedy"); ob.rollout(7, 1)
+            env.rollout(9, "random"); ob.rollout(9, 0)
+            _compare_state(env, ob)
+            feats, valid, count = env.get_after_states(include_terminal=True)
+            of, ov, oc, on = ob.afterstates()
+            mask = np.arange(env.a_max)[None, :] < on[:, None]
+            assert np.array_equal(feats.cpu().numpy()[mask], (of * dirs)[mask])
+            assert np.array_equal(np.signbit(feats.cpu().numpy()[mask]), np.signbit((of * dirs)[mask]))   # -0.0 where 0 * -1
+            assert np.array_equal(valid.cpu().numpy().view(np.uint64), ov) and np.array_equal(count.cpu().numpy(), oc)
+            a = (np.arange(n) * 7 % np.maximum(oc, 1)).astype(np.int32)
+            obs, rew, done, lines = env.step(a, auto_reset=True)
+            oobs, orew, odone, olines = ob.step(a, auto_reset=True)
+            assert np.array_equal(obs.cpu().numpy(), oobs * dirs) and np.array_equal(rew.cpu().numpy(), orew)
+            assert np.array_equal(done.cpu().numpy(), odone) and np.array_equal(lines.cpu().numpy(), olines)

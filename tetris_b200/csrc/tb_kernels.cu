@@ -306,8 +306,8 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             load_board<C, R>(sv, e, col);
             const Meta mt = unpack_meta(sv.meta[e]);
             build_env<C, R>(col, sm.run, sm.rec + tid * K::WORDS);
-            sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
-            sm.pid[tid] = (uint8_t)mt.piece;
+            if (mt.piece < kNumPieces) sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
+            sm.pid[tid] = (uint8_t)min(mt.piece, kNumPieces - 1);       // finished forks (piece 0xFF/0xFE): no afterstates
         }
         __syncthreads();
         if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
@@ -337,9 +337,9 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                     if (on) {
                         Eval ev;
                         const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
-                        if (status == kFastDone) emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs);
-                        else if (status == kFastClears) slow = !ev.terminal || want_terminal;
-                        else slow = want_terminal;
+                        if (status == kFastDone) { if (slot < a_stride) emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs); }
+                        else if (status == kFastClears) slow = (!ev.terminal || want_terminal) && slot < a_stride;
+                        else slow = want_terminal && slot < a_stride;
                         legal = !ev.terminal;
                     }
                     vsel |= ((__ballot_sync(FULLMASK, legal) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
@@ -455,11 +455,12 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
     load_board<C, R>(sv, e, col);
     Meta mt = unpack_meta(sv.meta[e]);
     uint2 ep = sv.epi[e];
-    const uint32_t pw = s_piece[mt.piece];
+    const bool live = mt.piece < kNumPieces;                                  // not a finished rollout fork
+    const uint32_t pw = s_piece[live ? mt.piece : 0];
     const int n_slots = piece_num_slots(pw, C);
     const int action = actions[e];
     int sel = -1;
-    if (action >= 0) {
+    if (action >= 0 && live) {
         if (flags & TB_FLAG_ACTION_IS_SLOT) {
             if (action < n_slots) {
                 int ori, c;
