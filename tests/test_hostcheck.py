@@ -22,7 +22,7 @@ SHAPES = [(10, 20), (10, 10), (6, 12), (8, 16), (4, 4)]
 def hc():
     if (not os.path.exists(SO)) or max(os.path.getmtime(SRC), os.path.getmtime(CORE)) > os.path.getmtime(SO):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-Wno-unknown-pragmas", "-o", SO, SRC])
+                               "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-o", SO, SRC])
     L = C.CDLL(SO)
     L.hc_afterstates.restype = C.c_int
     L.hc_afterstates.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_int] + [C.c_void_p] * 6

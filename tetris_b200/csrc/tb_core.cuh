@@ -598,6 +598,61 @@ TB_HD void build_env(const uint32_t *col, const uint16_t *runtab, uint32_t *rec)
     rec[K::T_HMAX] = (uint32_t)height_of(any);
 }
 
+// The same record, built by a rolled loop over the columns already stored in rec[COLX + 2 ..] -- an eighth of the
+// code of the unrolled form above (instruction-cache footprint matters more than the few extra shared-memory
+// accesses: K1 / K3 are instruction-latency bound).  Precondition as above.
+template <int C, int R>
+TB_HD void build_env_rolled(const uint16_t *runtab, uint32_t *rec)
+{
+    using S = Shape<C, R>;
+    using K = Env<C, R>;
+    uint8_t *rb = reinterpret_cast<uint8_t *>(rec);
+    uint16_t *rh = reinterpret_cast<uint16_t *>(rec);
+    rec[K::COLX + 0] = 0u; rec[K::COLX + 1] = S::ALL;
+    rec[K::COLX + C + 2] = S::ALL; rec[K::COLX + C + 3] = 0u;
+    rb[4 * K::H8 + 0] = (uint8_t)R; rb[4 * K::H8 + C + 1] = (uint8_t)R;
+    rh[2 * K::PW16 + 0] = 0; rh[2 * K::PW16 + 1] = 0; rh[2 * K::PRT16 + 0] = 0;
+    int holes = 0, ct = 0, hd = 0, wells = 0, rt = 0, hL = R;
+    uint32_t hm = 0, L = S::ALL, any = 0, acc = S::ALL;
+    uint32_t x = rec[K::COLX + 2];
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        const uint32_t Rt = rec[K::COLX + 3 + c];                  // column c + 1, or the right wall sentinel
+        rec[K::PAND + c] = acc;
+        acc &= x;
+        const int h = height_of(x);
+        const uint32_t mh = mask_lo(h);
+        const uint32_t hole = ~x & mh;
+        holes += popc32(hole);
+        hm |= hole;
+        any |= x;
+        uint32_t t = hole & (x >> 1);
+        const int nr = popc32(t);
+        ct += 1 + 2 * nr;
+        while (t) { const int r = ctz32(t); hd += popc32(x >> (r + 1)); t &= t - 1; }
+        wells += run_sum_tab<R>(runtab, L & Rt & ~x);
+        if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh);
+        else rt += popc32(L & mask_lo(hL));
+        rb[4 * K::H8 + c + 1] = (uint8_t)h;
+        rb[4 * K::NR8 + c] = (uint8_t)nr;
+        rh[2 * K::PW16 + c + 2] = (uint16_t)wells;
+        rh[2 * K::PRT16 + c + 1] = (uint16_t)rt;
+        L = x; hL = h; x = Rt;
+    }
+    rec[K::PAND + C] = acc;
+    rh[2 * K::PW16 + C + 2] = (uint16_t)wells;
+    rh[2 * K::PRT16 + C + 1] = (uint16_t)rt;
+    rt += R - popc32(L);                                           // L = column C-1 after the loop
+    acc = S::ALL;
+    rec[K::SAND + C] = acc;
+#pragma unroll 1
+    for (int c = C - 1; c >= 0; --c) { acc &= rec[K::COLX + 2 + c]; rec[K::SAND + c] = acc; }
+    rec[K::T_CT] = kFloatBias + (uint32_t)ct; rec[K::T_HD] = kFloatBias + (uint32_t)hd;
+    rec[K::T_WELLS] = kFloatBias + (uint32_t)wells; rec[K::T_RT] = kFloatBias + (uint32_t)rt;
+    rec[K::T_HOLES] = kFloatBias + (uint32_t)holes; rec[K::T_HM] = hm;
+    rec[K::T_HMAX] = (uint32_t)height_of(any);
+}
+
 // eval_placement status
 constexpr int kFastDone = 0;      // features written, afterstate is legal
 constexpr int kFastClears = 1;    // a line clears: features need the general path; e.a / e.full / e.terminal are set

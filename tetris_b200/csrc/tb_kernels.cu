@@ -305,7 +305,10 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             uint32_t col[C];
             load_board<C, R>(sv, e, col);
             const Meta mt = unpack_meta(sv.meta[e]);
-            build_env<C, R>(col, sm.run, sm.rec + tid * K::WORDS);
+            uint32_t *myrec = sm.rec + tid * K::WORDS;
+#pragma unroll
+            for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
+            build_env_rolled<C, R>(sm.run, myrec);
             if (mt.piece < kNumPieces) sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
             sm.pid[tid] = (uint8_t)min(mt.piece, kNumPieces - 1);       // finished forks (piece 0xFF/0xFE): no afterstates
         }
@@ -705,10 +708,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             bs.best[tid] = 0ull;
             int n_slots = 0;
             if (active) {
-                uint32_t col[C];
-#pragma unroll
-                for (int i = 0; i < C; ++i) col[i] = myrec[K::COLX + 2 + i];
-                build_env<C, R>(col, sm.run, myrec);
+                build_env_rolled<C, R>(sm.run, myrec);         // the columns are already in the record
                 sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
                 sm.pid[tid] = (uint8_t)mt.piece;
                 n_slots = piece_num_slots(sm.piece[mt.piece], C);
@@ -1116,7 +1116,11 @@ __global__ void k_action_probs(int64_t n, int a_stride, const float *__restrict_
 using namespace tb;
 
 // board shapes compiled in: the three of BASELINE.json's configs plus two extras (mid-size, tiny edge case)
+#ifdef TB_ONLY_10x20   /* quick experimental builds: nvcc -DTB_ONLY_10x20 */
+#define TB_SHAPES(X) X(10, 20)
+#else
 #define TB_SHAPES(X) X(10, 20) X(10, 10) X(6, 12) X(8, 16) X(4, 4)
+#endif
 
 static thread_local char g_err[256] = "";
 static int fail(const char *fmt, const char *detail)
