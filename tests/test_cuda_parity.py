@@ -393,3 +393,24 @@ def test_ragged_sizes(n):
             oobs, orew, odone, olines = ob.step(a, auto_reset=True)
             assert np.array_equal(obs.cpu().numpy(), oobs * dirs) and np.array_equal(rew.cpu().numpy(), orew)
             assert np.array_equal(done.cpu().numpy(), odone) and np.array_equal(lines.cpu().numpy(), olines)
+
+
+@pytest.mark.parametrize("shape,steps", [((10, 20), 1200), ((10, 10), 1500), ((4, 4), 1500)])
+def test_long_greedy_rollout_subset(shape, steps):
+    """Long fused rollouts (many episodes per env on the small boards, thousands of line clears, queue overflows on 4x4)
+    on 20,000 envs; envs are independent and their RNG is keyed by the global env id, so the oracle replays only the
+    first 192 envs and must end on identical boards, pieces and episode counters."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    Cc, R = shape
+    n, m, seed = 20000, 192, 4242
+    env = BatchedTetris(Cc, R, n, piece_set=1, seed=seed)
+    ob = orc.Batch(Cc, R, m, piece_set=1, seed=seed)
+    ob.reset()
+    for chunk in (steps // 3, steps - steps // 3):
+        env.rollout(chunk, "greedy")
+        ob.rollout(chunk, 1, threads=8)
+    rows, heights, piece = env.export_boards(0, m)
+    assert np.array_equal(rows.cpu().numpy().view(np.uint16), ob.rows())
+    assert np.array_equal(heights.cpu().numpy(), ob.heights) and np.array_equal(piece.cpu().numpy(), ob.piece)
+    assert int(env.stats[0]) == n * steps
