@@ -1,6 +1,6 @@
 #!/bin/bash
 # quick GPU check: parity tests + bench line (no extras) + K1/K3 timing under the tuning configs
-python -m pytest tests/test_cuda_parity.py -x -q 2>&1 | tail -5
+[ -n "$TB_SO_PATH" ] || python -m pytest tests/test_cuda_parity.py -x -q 2>&1 | tail -5
 for cfg in ${K1CFGS:-0 1 2}; do TB_K1_CFG=$cfg python - <<'PY'
 import os, torch
 from tetris_b200 import BatchedTetris

@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libtetris_b200.so")
+SO_PATH = os.environ.get("TB_SO_PATH") or os.path.join(CSRC, "libtetris_b200.so")   # override: experiments only
 SOURCES = [os.path.join(CSRC, "tb_kernels.cu"), os.path.join(CSRC, "tb_core.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "tetris_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -721,7 +721,9 @@ static_assert(sizeof(OriU) == 27 * 4, "OriU is 27 words");
 // Incremental evaluation of one placement: orientation `u` (width W) anchored at column c.  Only the piece's
 // columns and their neighbours are re-evaluated; everything else comes from the env record.  Branch-free apart
 // from the two early exits.
-template <int C, int R, int W>
+// LOWHALF (device only): when no lane of the warp has a well cell in the upper half of the board -- the usual case on
+// boards under greedy play -- the cumulative-wells lookups reduce to one table access per column.
+template <int C, int R, int W, bool LOWHALF = false>
 TB_HD int eval_neigh(const uint32_t *rec, const uint16_t *runtab, const Neigh<C, R, W> &nb, const OriU &u, int c, Eval &e)
 {
     using K = Env<C, R>;
@@ -765,8 +767,24 @@ TB_HD int eval_neigh(const uint32_t *rec, const uint16_t *runtab, const Neigh<C,
 
     // wells over columns c-1 .. c+W, row transitions over columns c .. c+W; the sentinels make the walls come out right
     uint32_t wells = nb.wells0, rt = nb.rt0;
+#if defined(__CUDA_ARCH__)
+    if (LOWHALF) {
+        uint32_t wm[W + 2], hi = 0u;
 #pragma unroll
-    for (int k = 1; k <= W + 2; ++k) wells += (uint32_t)run_sum_tab<R>(runtab, y[k - 1] & y[k + 1] & ~y[k]);
+        for (int k = 1; k <= W + 2; ++k) { wm[k - 1] = y[k - 1] & y[k + 1] & ~y[k]; hi |= wm[k - 1]; }
+        if (__any_sync(__activemask(), (hi >> RunTab<R>::HB) != 0u)) {
+#pragma unroll
+            for (int k = 0; k < W + 2; ++k) wells += (uint32_t)run_sum_tab<R>(runtab, wm[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < W + 2; ++k) wells += (uint32_t)(runtab[wm[k]] & 127u);
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int k = 1; k <= W + 2; ++k) wells += (uint32_t)run_sum_tab<R>(runtab, y[k - 1] & y[k + 1] & ~y[k]);
+    }
 #pragma unroll
     for (int dx = 0; dx < W; ++dx) {                               // piece columns: height > 0
         const int hj = h[1 + dx], hl = h[dx];

@@ -741,7 +741,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                         bool slow = false;
                         if (on) {
                             Eval ev;
-                            const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
+                            const int status = eval_neigh<C, R, W, true>(rec, sm.run, nb, u, c, ev);
                             if (status == kFastDone) {
                                 const uint32_t ord = orderable(fitness(ev.f, wts.v));         // game.py:109-120
                                 if (ord > best_ord) { best_ord = ord; best_slot = slot; }     // slots ascend with o
