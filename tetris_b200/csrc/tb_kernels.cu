@@ -217,8 +217,9 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
         const uint32_t pw = c_piece[p];
         const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
         const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase, sbase = l ? n0 * (C - w0 + 1) : 0;
-        sm.job[threadIdx.x] = (uint32_t)p | (uint32_t)l << 4 | (uint32_t)w << 5 | (uint32_t)(w <= C ? n : 0) << 8 |
-                              (uint32_t)ob << 10 | (uint32_t)sbase << 16;
+        const uint32_t jb = (uint32_t)p | (uint32_t)l << 4 | (uint32_t)w << 5 | (uint32_t)(w <= C ? n : 0) << 8 |
+                            (uint32_t)ob << 10 | (uint32_t)sbase << 16;
+        sm.job[threadIdx.x] = jb;
     }
     if (threadIdx.x <= kNumPieces) { sm.cnt[0][threadIdx.x] = 0; sm.cnt[1][threadIdx.x] = 0; }
     for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = run_tab_entry<R>((uint32_t)m);
