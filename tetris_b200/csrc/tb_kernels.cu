@@ -11,7 +11,7 @@
 // the env record, applying a placement, RNG, game-over) runs one lane per env; per-afterstate work runs one
 // lane per (env, slot) item over the tile's flattened item list (~23 items per env on average), so lanes
 // stay busy although pieces have 9..34 placements.  Placements that clear a line or reach the top are
-// rare and costly (from-scratch evaluation): they are queued in shared memory and evaluated 32 at a time
+// rare and costly (from-scratch evaluation): they are marked in per-env bit masks and evaluated 32 at a time
 // instead of diverging the common incremental path.
 //
 // HBM layout: see include/tetris_b200.h (row masks, 8 rows per 128-bit word, SoA over envs -> every global
@@ -176,9 +176,8 @@ k_reset(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const ui
 // orientations in a warp-uniform loop, so the orientation descriptor is uniform, every loop over the piece's
 // columns has a uniform trip count, and the neighbourhood loads are shared by the orientations of a column loop.
 // Placements that clear a line only need the general evaluation for their FEATURES (legality follows from the
-// full-row count); they go to a CTA-wide queue and are evaluated one thread per item in phase S.
+// full-row count); they are marked in per-env bit masks and evaluated one lane per item in phase S.
 // ---------------------------------------------------------------------------------------------
-constexpr int QWARP = 64;            // slow-path queue entries per warp
 constexpr int kNumJobs = 2 * kNumPieces;
 
 template <int C, int R, int TILE>
@@ -188,18 +187,22 @@ struct CtaSmem {
     uint32_t odesc[kNumOris][kOriWords]; // orientation descriptors, decoded (OriU): broadcast 128-bit loads
     uint32_t vloc[TILE][2];              // K1: legal placements of each env per column loop (16 bits per orientation)
                                          // K3: best orderable score of each env per column loop
-    uint16_t queue[TILE / 32][QWARP];    // per warp: line-clearing placements, env << 6 | slot
+    uint32_t sloc[TILE][2];              // placements of each env that need the general evaluation (they clear a line),
+                                         // per column loop, same bit layout as vloc in K1 (16 bits per orientation)
     uint16_t run[RunTab<R>::SIZE];
     uint8_t list[kNumPieces][TILE];      // tile-local env indices grouped by piece
     uint8_t pid[TILE];                   // piece of each env of the tile
-    uint8_t bslot[TILE][2];              // K3: slot of the best score per column loop
     int cnt[2][kNumPieces + 1];          // envs per piece, double-buffered by tile / step parity
     uint32_t job[kNumJobs];              // (piece, column loop): p | l << 4 | w << 5 | n << 8 | ob << 10 | sbase << 16
     uint32_t ori[32], piece[16];
 };
 // K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements,
 // and per-warp episode statistics
-template <int TILE> struct BestSmem { unsigned long long best[TILE]; long long wstat[TILE / 32][TB_ST_COUNT]; };
+template <int TILE> struct BestSmem {
+    unsigned long long best[TILE];
+    long long wstat[TILE / 32][TB_ST_COUNT];
+    uint8_t bslot[TILE][2];              // slot of the best score per column loop
+};
 
 template <int C, int R, int TILE>
 __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
@@ -226,18 +229,39 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
     __syncthreads();
 }
 
-// Append `packed` of the flagged lanes to the warp's queue.  Returns false for a lane whose item did not fit
-// (the caller evaluates it in place).  qn is warp-uniform.
-__device__ __forceinline__ bool queue_push(uint16_t *queue, int &qn, bool flag, uint32_t packed, int lane)
+// Phase S work distribution.  Every lane owns one env of the warp's 32 and holds that env's slow-placement masks
+// (m0, m1: column loops 0 / 1, bit 16 * o + c).  The set bits of all 32 envs are flattened over the lanes, 32 items per
+// pass, so the general evaluation runs with full warps however the items are spread over the envs.
+// f(owner lane, loop l, orientation o in the loop, column c) is called for every item by one lane.
+template <typename F>
+__device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int lane, F &&f)
 {
-    const unsigned bal = __ballot_sync(FULLMASK, flag);
-    if (bal == 0u) return true;
-    const int pos = qn + __popc(bal & ((1u << lane) - 1u));
-    qn += __popc(bal);
-    if (!flag) return true;
-    if (pos >= QWARP) return false;
-    queue[pos] = (uint16_t)packed;
-    return true;
+    const int cnt = __popc(m0) + __popc(m1);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(FULLMASK, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(FULLMASK, incl, 31);
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        int owner = 0;                                     // first lane whose inclusive prefix exceeds i
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const int v = __shfl_sync(FULLMASK, incl, owner + step - 1);
+            if (v <= i) owner += step;
+        }
+        owner &= 31;
+        const int before = __shfl_sync(FULLMASK, incl - cnt, owner);
+        const uint32_t om0 = __shfl_sync(FULLMASK, m0, owner), om1 = __shfl_sync(FULLMASK, m1, owner);
+        if (i < total) {
+            const int r = i - before, p0 = __popc(om0);
+            const int l = r >= p0;
+            const int b = (int)__fns(l ? om1 : om0, 0u, (l ? r - p0 : r) + 1);
+            f(owner, l, b >> 4, b & 15);
+        }
+    }
 }
 
 // insert a zero above every one of the low 16 bits
@@ -274,13 +298,6 @@ __device__ __forceinline__ float *feat_row(float *__restrict__ feats, int64_t en
 
 template <int V> struct IntC { static constexpr int value = V; };
 
-// general (from-scratch) evaluation kept out of line: it is the rare path and would otherwise be inlined per orientation
-template <int C, int R>
-__device__ __noinline__ void eval_slow_outofline(const uint32_t *col, uint32_t d, int c, Eval *ev)
-{
-    eval_slow<C, R>(col, d, c, *ev, nullptr);
-}
-
 template <int C, int R, bool DIRS, int TILE>
 __device__ __forceinline__ void
 afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
@@ -294,7 +311,6 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool want_terminal = (flags & TB_FLAG_INCLUDE_TERMINAL) != 0;
     const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
-    uint16_t *queue = sm.queue[warp];
     int par = 0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
@@ -302,6 +318,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
         int *cnt = sm.cnt[par];
         // ---- phase A (thread per env).  cnt[par] was zeroed during the previous tile's phase B.
         sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
+        sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
         if (e < sv.n_env) {
             uint32_t col[C];
             load_board<C, R>(sv, e, col);
@@ -316,7 +333,6 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
         __syncthreads();
         if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
         // ---- phase B (warp per window): per (piece, column loop) job; a window = EPW envs x (C - W + 1) columns
-        int qn = 0;
         auto column_loop = [&](auto wtag, uint32_t jb, int np) {
             constexpr int W = decltype(wtag)::value;
             constexpr int NC = C - W + 1, EPW = 32 / NC;
@@ -331,7 +347,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 const uint32_t *rec = sm.rec + env * K::WORDS;
                 Neigh<C, R, W> nb;
                 load_neigh<C, R, W>(rec, c, nb);
-                uint32_t vsel = 0u;                         // leader lane: legal columns of its env, 16 bits per orientation
+                uint32_t vsel = 0u, ssel = 0u;              // leader lane: legal / slow columns of its env, 16 bits per orientation
 #pragma unroll 1
                 for (int o = 0; o < n; ++o) {
                     const int oi = (int)((jb >> 10) & 63u) + o;
@@ -347,13 +363,9 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                         legal = !ev.terminal;
                     }
                     vsel |= ((__ballot_sync(FULLMASK, legal) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
-                    if (!queue_push(queue, qn, slow, (uint32_t)(env << 6 | slot), lane)) {
-                        Eval e2;                            // queue full: evaluate in place
-                        eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[oi], c, &e2);
-                        emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), e2, dirs);
-                    }
+                    ssel |= ((__ballot_sync(FULLMASK, slow) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
                 }
-                if (on && c == 0) sm.vloc[env][l] = vsel;
+                if (on && c == 0) { sm.vloc[env][l] = vsel; sm.sloc[env][l] = ssel; }
             }
         };
 #pragma unroll 1
@@ -368,18 +380,19 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np); break;
             }
         }
-        // ---- phase S: this warp's line-clearing placements, one lane per item, general evaluation
-        __syncwarp();
-        for (int i = lane; i < min(qn, QWARP); i += 32) {
-            const uint32_t packed = queue[i];
-            const int env = (int)(packed >> 6), slot = (int)(packed & 63u);
-            int ori, cc;
-            slot_to_placement(sm.piece[sm.pid[env]], C, slot, ori, cc);
+        __syncthreads();                                   // every warp is done with phase B: vloc / sloc are complete
+        // ---- phase S: the placements that need the general evaluation (they clear a line), of this warp's own 32 envs,
+        // one lane per item.  Only warp-local data from here to the next tile's phase A: no further CTA barrier.
+        for_each_slow_item(sm.sloc[tid][0], sm.sloc[tid][1], lane, [&](int owner, int l, int o, int cc) {
+            const int env = (warp << 5) + owner;
+            const uint32_t pw = sm.piece[sm.pid[env]];
+            const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
+            const int slot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
             Eval ev;
-            eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[ori], cc, ev, nullptr);
+            eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
             emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs);
-        }
-        __syncthreads();                                   // every warp is done with rec / list; vloc is complete
+        });
+        __syncwarp();
         // ---- legal-action masks, thread per env (coalesced)
         if (e < sv.n_env) {
             const uint32_t pw = sm.piece[sm.pid[tid]];
@@ -676,7 +689,6 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
     stage_cta(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
-    uint16_t *queue = sm.queue[warp];
     long long *wstat = bs.wstat[warp];
     if (lane < TB_ST_COUNT) wstat[lane] = 0;
     int par = 0;
@@ -706,6 +718,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             int *cnt = sm.cnt[par];
             // ---- phase A (thread per env).  cnt[par] was zeroed during the previous step's phase B.
             sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
+            sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
             bs.best[tid] = 0ull;
             int n_slots = 0;
             if (active) {
@@ -717,7 +730,6 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             __syncthreads();
             if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
             // ---- phase B: score every legal placement, keep the first arg-max per env and column loop
-            int qn = 0;
             auto column_loop = [&](auto wtag, uint32_t jb, int np) {
                 constexpr int W = decltype(wtag)::value;
                 constexpr int NC = C - W + 1, EPW = 32 / NC;
@@ -734,6 +746,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     load_neigh<C, R, W>(rec, c, nb);
                     uint32_t best_ord = 0u;                // this lane's best orderable score (0 = none) and its slot
                     int best_slot = 0;
+                    uint32_t ssel = 0u;                    // leader lane: line-clearing legal placements of its env
 #pragma unroll 1
                     for (int o = 0; o < n; ++o) {
                         const int oi = (int)((jb >> 10) & 63u) + o;
@@ -750,11 +763,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                                 slow = !ev.terminal;
                             }
                         }
-                        if (!queue_push(queue, qn, slow, (uint32_t)(env << 6 | slot), lane)) {
-                            Eval e2;                        // queue full: evaluate in place
-                            eval_slow_outofline<C, R>(rec + K::COLX + 2, sm.ori[oi], c, &e2);
-                            atomicMax(&bs.best[env], score_key(orderable(fitness(e2.f, wts.v)), slot));
-                        }
+                        ssel |= ((__ballot_sync(FULLMASK, slow) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
                     }
                     // first arg-max over the env's NC lanes: highest score, then lowest slot (= lowest column, then o)
                     uint32_t m = best_ord;
@@ -767,7 +776,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     const uint32_t hit = (__ballot_sync(FULLMASK, best_ord == m) >> (k * NC)) & ((1u << NC) - 1u);
                     const int src = k * NC + __ffs((int)hit) - 1;              // lowest column that reaches it
                     const int sl = __shfl_sync(FULLMASK, best_slot, src & 31);
-                    if (on && c == 0) { sm.vloc[env][l] = m; sm.bslot[env][l] = (uint8_t)sl; }
+                    if (on && c == 0) { sm.vloc[env][l] = m; bs.bslot[env][l] = (uint8_t)sl; sm.sloc[env][l] = ssel; }
                 }
             };
 #pragma unroll 1
@@ -782,18 +791,18 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np); break;
                 }
             }
-            // ---- phase S: this warp's line-clearing placements
-            __syncwarp();
-            for (int i = lane; i < min(qn, QWARP); i += 32) {
-                const uint32_t packed = queue[i];
-                const int env = (int)(packed >> 6), slot = (int)(packed & 63u);
-                int ori, cc;
-                slot_to_placement(sm.piece[sm.pid[env]], C, slot, ori, cc);
+            __syncthreads();                               // phase B is complete: vloc / bslot / sloc of every env
+            // ---- phase S: the line-clearing legal placements of this warp's own 32 envs, one lane per item
+            for_each_slow_item(sm.sloc[tid][0], sm.sloc[tid][1], lane, [&](int owner, int l, int o, int cc) {
+                const int env = (warp << 5) + owner;
+                const uint32_t pw = sm.piece[sm.pid[env]];
+                const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
+                const int slot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
                 Eval ev;
-                eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[ori], cc, ev, nullptr);
+                eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
                 atomicMax(&bs.best[env], score_key(orderable(fitness(ev.f, wts.v)), slot));
-            }
-            __syncthreads();
+            });
+            __syncwarp();                                  // phase C reads the best keys of this warp's envs only
             // ---- phase C (thread per env): apply the choice, draw the next piece, game over / auto-reset
             int lc = 0;
             bool placed = false, dn = false;
@@ -808,7 +817,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 for (int l = 0; l < 2; ++l) {
                     const uint32_t m = sm.vloc[tid][l];
                     if (m != 0u) {
-                        const unsigned long long k64 = score_key(m, (int)sm.bslot[tid][l]);
+                        const unsigned long long k64 = score_key(m, (int)bs.bslot[tid][l]);
                         best = k64 > best ? k64 : best;
                     }
                 }
