@@ -356,7 +356,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                     bool slow = false, legal = false;
                     if (on) {
                         Eval ev;
-                        const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
+                        const int status = eval_neigh<C, R, W, true>(rec, sm.run, nb, u, c, ev);
                         if (status == kFastDone) { if (slot < a_stride) emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs); }
                         else if (status == kFastClears) slow = (!ev.terminal || want_terminal) && slot < a_stride;
                         else slow = want_terminal && slot < a_stride;
