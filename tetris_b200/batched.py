@@ -199,9 +199,13 @@ class BatchedTetris:
         return rows, heights, piece
 
     def import_boards(self, rows, piece=None, first=0):
-        """Upload boards as row masks (uint16 per row, bit c = column c); heights are recomputed on the device."""
-        r = np.ascontiguousarray(rows.cpu().numpy() if isinstance(rows, torch.Tensor) else rows).astype(np.uint16)
-        r = torch.as_tensor(r.view(np.int16), device=self.device)
+        """Upload boards as row masks (uint16 per row, bit c = column c); heights are recomputed on the device.
+        rows: numpy / torch array [count, num_rows + 4] (a CUDA int16 tensor is used in place, no host round trip)."""
+        if isinstance(rows, torch.Tensor) and rows.is_cuda and rows.dtype == torch.int16:
+            r = rows.contiguous()
+        else:
+            r = np.ascontiguousarray(rows.cpu().numpy() if isinstance(rows, torch.Tensor) else rows).astype(np.uint16)
+            r = torch.as_tensor(r.view(np.int16), device=self.device)
         if r.dim() != 2 or r.shape[1] != self.n_stored_rows:
             raise ValueError("rows must have shape (count, num_rows + 4)")
         p = self._dev_u8(piece)
