@@ -522,87 +522,11 @@ struct Env {
     static constexpr int WORDS = WORDS_RAW | 1;            // odd stride: records of different envs spread over banks
 };
 
-// Precondition: every column height is <= R (a non-terminal state).
+// Builds the record from the columns already stored in rec[COLX + 2 .. COLX + 2 + C).  A rolled loop on purpose: an
+// unrolled builder is 8x the code, and instruction-cache footprint matters more than a few extra shared-memory
+// accesses (K1 / K3 are instruction-latency bound).  Precondition: every column height is <= R (non-terminal state).
 template <int C, int R>
-TB_HD void build_env(const uint32_t *col, const uint16_t *runtab, uint32_t *rec)
-{
-    using S = Shape<C, R>;
-    using K = Env<C, R>;
-    rec[K::COLX + 0] = 0u; rec[K::COLX + 1] = S::ALL;
-#pragma unroll
-    for (int c = 0; c < C; ++c) rec[K::COLX + 2 + c] = col[c];
-    rec[K::COLX + C + 2] = S::ALL; rec[K::COLX + C + 3] = 0u;
-    uint32_t acc = S::ALL;
-#pragma unroll
-    for (int c = 0; c < C; ++c) { rec[K::PAND + c] = acc; acc &= col[c]; }
-    rec[K::PAND + C] = acc;
-    acc = S::ALL;
-    rec[K::SAND + C] = acc;
-#pragma unroll
-    for (int c = C - 1; c >= 0; --c) { acc &= col[c]; rec[K::SAND + c] = acc; }
-
-    constexpr int NH = (C + 2 + 3) / 4, NN = (C + 3) / 4, NPW = (C + 3 + 1) / 2, NPR = (C + 2 + 1) / 2;
-    uint32_t h8[NH], nr8[NN], pw[NPW], prt[NPR];
-#pragma unroll
-    for (int i = 0; i < NH; ++i) h8[i] = 0;
-#pragma unroll
-    for (int i = 0; i < NN; ++i) nr8[i] = 0;
-#pragma unroll
-    for (int i = 0; i < NPW; ++i) pw[i] = 0;
-#pragma unroll
-    for (int i = 0; i < NPR; ++i) prt[i] = 0;
-    h8[0] = (uint32_t)R;
-    h8[(C + 1) >> 2] |= (uint32_t)R << (8 * ((C + 1) & 3));
-    int holes = 0, ct = 0, hd = 0, wells = 0, rt = 0;
-    uint32_t hm = 0, L = S::ALL, any = 0;
-    int hL = R;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const uint32_t x = col[c];
-        const int h = height_of(x);
-        const uint32_t Rt = (c + 1 < C) ? col[c + 1] : S::ALL;
-        const uint32_t mh = mask_lo(h);
-        const uint32_t hole = ~x & mh;
-        holes += popc32(hole);
-        hm |= hole;
-        any |= x;
-        uint32_t t = hole & (x >> 1);
-        const int nr = popc32(t);
-        ct += 1 + 2 * nr;
-        while (t) { const int r = ctz32(t); hd += popc32(x >> (r + 1)); t &= t - 1; }
-        // heights <= R: the well cells of the column are exactly ~x & L & Rt (state.py:222-233,256-272)
-        wells += run_sum_tab<R>(runtab, L & Rt & ~x);
-        if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh);
-        else rt += popc32(L & mask_lo(hL));
-        h8[(c + 1) >> 2] |= (uint32_t)h << (8 * ((c + 1) & 3));
-        nr8[c >> 2] |= (uint32_t)nr << (8 * (c & 3));
-        // PW16[i] = wells of columns < clamp(i-1, 0, C): after column c the running sum belongs at i = c + 2
-        pw[(c + 2) >> 1] |= (uint32_t)wells << (16 * ((c + 2) & 1));
-        prt[(c + 1) >> 1] |= (uint32_t)rt << (16 * ((c + 1) & 1));
-        L = x; hL = h;
-    }
-    pw[(C + 2) >> 1] |= (uint32_t)wells << (16 * ((C + 2) & 1));     // i = C + 2 clamps to C
-    prt[(C + 1) >> 1] |= (uint32_t)rt << (16 * ((C + 1) & 1));       // i = C + 1 clamps to C
-    rt += R - popc32(col[C - 1]);
-#pragma unroll
-    for (int i = 0; i < NH; ++i) rec[K::H8 + i] = h8[i];
-#pragma unroll
-    for (int i = 0; i < NN; ++i) rec[K::NR8 + i] = nr8[i];
-#pragma unroll
-    for (int i = 0; i < NPW; ++i) rec[K::PW16 + i] = pw[i];
-#pragma unroll
-    for (int i = 0; i < NPR; ++i) rec[K::PRT16 + i] = prt[i];
-    rec[K::T_CT] = kFloatBias + (uint32_t)ct; rec[K::T_HD] = kFloatBias + (uint32_t)hd;
-    rec[K::T_WELLS] = kFloatBias + (uint32_t)wells; rec[K::T_RT] = kFloatBias + (uint32_t)rt;
-    rec[K::T_HOLES] = kFloatBias + (uint32_t)holes; rec[K::T_HM] = hm;
-    rec[K::T_HMAX] = (uint32_t)height_of(any);
-}
-
-// The same record, built by a rolled loop over the columns already stored in rec[COLX + 2 ..] -- an eighth of the
-// code of the unrolled form above (instruction-cache footprint matters more than the few extra shared-memory
-// accesses: K1 / K3 are instruction-latency bound).  Precondition as above.
-template <int C, int R>
-TB_HD void build_env_rolled(const uint16_t *runtab, uint32_t *rec)
+TB_HD void build_env(const uint16_t *runtab, uint32_t *rec)
 {
     using S = Shape<C, R>;
     using K = Env<C, R>;

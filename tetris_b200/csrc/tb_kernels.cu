@@ -7,12 +7,13 @@
 //   k_rollout_*    K3  example_play.py:11-21 loop fused with an in-kernel policy
 //
 // Mapping.  The work is integer/bit manipulation on a few dozen bytes per env -- no GEMM shape anywhere, so
-// no tensor cores.  Envs are independent; a warp owns a tile of 32 envs.  Per-env work (load + transpose,
-// the env record, applying a placement, RNG, game-over) runs one lane per env; per-afterstate work runs one
-// lane per (env, slot) item over the tile's flattened item list (~23 items per env on average), so lanes
-// stay busy although pieces have 9..34 placements.  Placements that clear a line or reach the top are
-// rare and costly (from-scratch evaluation): they are marked in per-env bit masks and evaluated 32 at a time
-// instead of diverging the common incremental path.
+// no tensor cores.  Envs are independent.  K1 / K3 give a CTA a tile of 256 envs: per-env work (load + transpose,
+// the env record, applying a placement, RNG, game-over) runs one thread per env; per-afterstate work runs in
+// windows of envs that hold the same piece, lane = (env of the window, anchor column), so the piece's orientation
+// loop and width are warp-uniform and lanes stay busy although pieces have 9..34 placements.  Placements that
+// clear a line are rare and costly (from-scratch evaluation): they are marked in per-env bit masks and evaluated
+// 32 at a time instead of diverging the common incremental path.  K2 and the random rollout are thread per env.
+// See DESIGN.md section 3.
 //
 // HBM layout: see include/tetris_b200.h (row masks, 8 rows per 128-bit word, SoA over envs -> every global
 // load/store of state is a coalesced 128-bit access).
@@ -326,7 +327,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             uint32_t *myrec = sm.rec + tid * K::WORDS;
 #pragma unroll
             for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
-            build_env_rolled<C, R>(sm.run, myrec);
+            build_env<C, R>(sm.run, myrec);
             if (mt.piece < kNumPieces) sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
             sm.pid[tid] = (uint8_t)min(mt.piece, kNumPieces - 1);       // finished forks (piece 0xFF/0xFE): no afterstates
         }
@@ -722,7 +723,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             bs.best[tid] = 0ull;
             int n_slots = 0;
             if (active) {
-                build_env_rolled<C, R>(sm.run, myrec);         // the columns are already in the record
+                build_env<C, R>(sm.run, myrec);         // the columns are already in the record
                 sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
                 sm.pid[tid] = (uint8_t)mt.piece;
                 n_slots = piece_num_slots(sm.piece[mt.piece], C);
