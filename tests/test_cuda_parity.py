@@ -414,3 +414,13 @@ def test_long_greedy_rollout_subset(shape, steps):
     assert np.array_equal(rows.cpu().numpy().view(np.uint16), ob.rows())
     assert np.array_equal(heights.cpu().numpy(), ob.heights) and np.array_equal(piece.cpu().numpy(), ob.piece)
     assert int(env.stats[0]) == n * steps
+
+
+def test_fuzz_against_oracle():
+    """tests/fuzz_gpu.py, 40 rounds: random seeds, env offsets, shapes, piece sets, policy weights and feature
+    directions; rollouts interleaved with afterstate / step comparisons.  (1500 rounds were run by hand.)"""
+    import fuzz_gpu
+    shapes = [(10, 20), (10, 10), (6, 12), (8, 16), (4, 4)]
+    for i in range(40):
+        Cc, R = shapes[i % len(shapes)]
+        fuzz_gpu.one(Cc, R, (i // len(shapes)) % 2, 7000 + i, [257, 1000, 3001, 513][i % 4])
