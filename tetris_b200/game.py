@@ -24,16 +24,12 @@ class Tetris:
 
     def __init__(self, num_columns, num_rows, feature_directions=None, feature_type='bcts', num_features=8,
                  tetromino_size=4):
-        self.feature_directions = feature_directions
-        self.num_columns = num_columns
-        self.num_rows = num_rows
-        self.feature_type = feature_type
-        self.num_features = num_features
-        self.tetromino_size = tetromino_size
+        self.num_columns, self.num_rows = num_columns, num_rows
+        self.feature_directions, self.feature_type, self.num_features = feature_directions, feature_type, num_features
+        self.tetromino_size = tetromino_size             # only sizes the buffer rows above the board (game.py:56)
 
         # reward = lines cleared + timestep_reward (+ loss_reward when the game ends), game.py:34-35,86-90
-        self.loss_reward = -100
-        self.timestep_reward = -1
+        self.loss_reward, self.timestep_reward = -100, -1
 
         # active piece set of the reference (game.py:38-39); assign `tetrominos` and `tetromino_sampler` to change
         # it, e.g. tetromino.standard_set(num_columns) for the seven tetrominoes of game.py:41-47
@@ -68,14 +64,13 @@ class Tetris:
 
     def step(self, action):
         """Take the action-th non-terminal afterstate of the last get_after_states() (game.py:82-92)."""
-        self.current_state = self.afterstates[action]
-        lines_cleared = self.current_state.n_cleared_lines
-        reward = lines_cleared + self.timestep_reward
-        self.current_tetromino = self.tetromino_sampler.next_tetromino()
-        done = self.is_game_over(self.current_state)
-        if done:
-            reward += self.loss_reward
-        return self.get_state(), reward, done, lines_cleared
+        chosen = self.afterstates[action]                 # IndexError / AttributeError exactly as in the reference
+        self.current_state = chosen
+        lines = chosen.n_cleared_lines
+        self.current_tetromino = self.tetromino_sampler.next_tetromino()      # drawn before the game-over test
+        done = self.is_game_over(chosen)
+        reward = lines + self.timestep_reward + (self.loss_reward if done else 0)
+        return self.get_state(), reward, done, lines
 
     def is_game_over(self, state):
         """True when the current piece has no non-terminal placement on `state` (game.py:94-100)."""
