@@ -420,6 +420,17 @@ def run_ours(args):
                 env4.step(a, auto_reset=True, check=False)
             torch.cuda.synchronize()
             out["lockstep_4096_placements_per_s"] = 4096 * 50 / (time.perf_counter() - t0)
+            # the same iteration captured once in a CUDA graph (launch-bound at this batch size)
+            envg = BatchedTetris(C, R, 4096, piece_set=PIECE_SET, seed=args.seed, device=dev)
+            replay, _outs = envg.capture_lockstep(           # default CUDA generator: graph-safe philox offsets
+                lambda f, v, c: (torch.randint(0, 2 ** 31 - 1, (4096,), device=dev) % c.long().clamp(min=1)).int())
+            for _ in range(10):
+                replay()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(200):
+                replay()
+            torch.cuda.synchronize()
+            out["lockstep_4096_cuda_graph_placements_per_s"] = 4096 * 200 / (time.perf_counter() - t0)
         except Exception as ex:
             out["random_policy_placements_per_s_per_gpu"] = repr(ex)
 

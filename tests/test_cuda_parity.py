@@ -424,3 +424,37 @@ def test_fuzz_against_oracle():
     for i in range(40):
         Cc, R = shapes[i % len(shapes)]
         fuzz_gpu.one(Cc, R, (i // len(shapes)) % 2, 7000 + i, [257, 1000, 3001, 513][i % 4])
+
+
+def test_cuda_graph_lockstep_equals_eager():
+    """BatchedTetris.capture_lockstep: the captured get_after_states -> policy -> step iteration replays to exactly
+    what the eager calls produce (same boards, rewards, dones) over many steps with game overs and auto-reset."""
+    torch = _torch()
+    from tetris_b200 import BatchedTetris
+    n = 4096
+    pol = lambda f, v, c: (torch.arange(n, device="cuda", dtype=torch.int64) * 7919 % c.long().clamp(min=1)).int()
+    a = BatchedTetris(10, 10, n, piece_set=1, seed=31)
+    b = BatchedTetris(10, 10, n, piece_set=1, seed=31)
+    replay, out = a.capture_lockstep(pol)
+    dones = 0
+    for t in range(120):
+        replay()
+        f, v, c = b.get_after_states()
+        obs, rew, done, lines = b.step(pol(f, v, c), auto_reset=True)
+        assert torch.equal(out["reward"], rew) and torch.equal(out["done"], done) and torch.equal(out["obs"], obs)
+        dones += int(done.sum())
+    assert np.array_equal(a.rows(), b.rows()) and np.array_equal(a.piece, b.piece) and dones > 0
+
+
+def test_batched_fitness():
+    torch = _torch()
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    env = BatchedTetris(10, 20, 500, piece_set=1, seed=2)
+    env.rollout(20, "random")
+    feats, valid, count = env.get_after_states(include_terminal=True)
+    s = env.fitness(feats).cpu().numpy()
+    f = feats.cpu().numpy()
+    for e in range(0, 500, 37):
+        for k in range(9):
+            assert s[e, k] == orc.fitness(f[e, k], orc.BCTS_WEIGHTS)

@@ -182,6 +182,47 @@ class BatchedTetris:
                                                           _ptr(probs), _ptr(grad), self._stream()))
         return probs if actions is None else (probs, grad)
 
+    def fitness(self, feats, weights=None):
+        """Tetris.fitness (game.py:109-120) for every row of `feats` (float32 [..., 8], contiguous, on this device):
+        float32 products summed left to right, no FMA.  Returns float32 [...]."""
+        w = np.ascontiguousarray(BCTS_WEIGHTS if weights is None else weights, dtype=np.float32)
+        f = feats.contiguous()
+        out = torch.empty(f.shape[:-1], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().tb_fitness(out.numel(), _ptr(f), w.ctypes.data_as(C.c_void_p), _ptr(out), self._stream()))
+        return out
+
+    def capture_lockstep(self, policy, auto_reset=True, include_terminal=False):
+        """Capture one lockstep iteration -- get_after_states -> policy -> step -- in a CUDA graph.
+
+        policy(feats, valid, count) -> int32 actions [n_env] must be made of capturable torch ops on this device
+        (no host synchronisation).  Returns (replay, outputs): replay() launches the whole iteration as one graph --
+        for small batches the iteration is launch-bound, this removes the per-kernel launch cost -- and `outputs` is
+        the dict of static tensors it fills (feats, valid, count, actions, obs, reward, done, lines)."""
+        out = {}
+        with torch.cuda.device(self.device):
+            feats = torch.empty((self.n_env, self.a_max, 8), dtype=torch.float32, device=self.device)
+            valid = torch.empty(self.n_env, dtype=torch.int64, device=self.device)
+            count = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
+
+            def iteration():
+                self.get_after_states(include_terminal=include_terminal, out=(feats, valid, count))
+                actions = policy(feats, valid, count).to(torch.int32)
+                obs, reward, done, lines = self.step(actions, auto_reset=auto_reset, check=False)
+                return actions, obs, reward, done, lines
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                   # warm-up off the capture stream (allocator, lazy init)
+                saved = self.state.clone()
+                iteration()
+                self.state.copy_(saved)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                actions, obs, reward, done, lines = iteration()
+        out.update(feats=feats, valid=valid, count=count, actions=actions, obs=obs, reward=reward, done=done, lines=lines)
+        return graph.replay, out
+
     def stats_dict(self, stats=None):
         s = (self.stats if stats is None else stats).cpu().tolist()
         return dict(zip(_lib.STATS, s))
