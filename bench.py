@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--rollout-steps", type=int, default=32, help="placements per env per step")
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--board", default="10x20", help="columns x rows: 10x20 (headline), 10x10, 6x12, 8x16")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="stream-pipelined chunks of the host-buffer e2e cycle")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu baseline / e2e side measurements")
     return ap.parse_args()
 
@@ -265,6 +266,46 @@ def run_ours(args):
         "dtype_note": "u32 column bit masks; features / scores leave the kernels as float32 (exact small integers, half-integers)",
     }
 
+    # ---- e2e through the public API with HOST buffers (every rank; whole-job value = all ranks' envs / max time).
+    # tetris_b200.HostRollout.play: every step the boards and pieces of all envs come from pinned host memory (H2D +
+    # tb_import_boards), are played T placements by the fused rollout, and go back to the host (tb_export_boards + D2H)
+    # together with the episode statistics -- the cycle of a caller that keeps its games on the host.  Copies, the two
+    # conversion kernels and the final synchronisation are inside the timed region.  The env range is cut into chunks on
+    # separate streams so the copies of one chunk overlap the rollout kernel of another.
+    e2e = e2e_serial = None
+    if not args.no_extras:
+        from tetris_b200 import HostRollout
+
+        def time_host_rollout(chunks):
+            hr = HostRollout(C, R, E, chunks=chunks, piece_set=PIECE_SET, seed=args.seed, env_offset=rank * E, device=dev)
+            for sub in hr.envs:
+                sub.rollout(30, "random")
+            hr.pull()
+            for _ in range(2):
+                hr.play(T, "greedy", weights)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                hr.play(T, "greedy", weights)                # synchronous: host buffers valid on return
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(world) * E * T * K / float(dt.item()), hr.h2d_bytes, hr.d2h_bytes
+
+        v, h2d, d2h = time_host_rollout(args.e2e_chunks)
+        e2e = {"value": v, "unit": "placements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "chunks": args.e2e_chunks,
+               "note": "HostRollout.play per step and rank: boards + pieces of all envs H2D from pinned memory -> "
+                       "tb_import_boards -> tb_rollout (T placements per env) -> tb_export_boards -> boards, heights, "
+                       "pieces and statistics D2H, synchronised; %d chunks on separate streams overlap copies with the "
+                       "kernel; whole-job value (all ranks, max time over ranks); bytes are per rank" % args.e2e_chunks}
+        if world == 1:
+            v1, _, _ = time_host_rollout(1)
+            e2e_serial = {"value": v1, "unit": "placements/s", "chunks": 1,
+                          "note": "the same cycle as one chunk on one stream (no copy/compute overlap)"}
+
     if rank == 0 and not args.no_extras:
         stats = env.stats_dict()
         out["rollout_afterstates_per_s_per_gpu"] = None
@@ -328,39 +369,10 @@ def run_ours(args):
         }
         del feats
 
-        # ---- e2e through the public API with HOST buffers: every step the boards and pieces of all envs come from pinned
-        # host memory (H2D + tb_import_boards), are played T placements by the fused rollout, and go back to the host
-        # (tb_export_boards + D2H) together with the episode statistics -- the cycle of a caller that keeps its games
-        # on the host.  Copies, the two conversion kernels and the final synchronisation are inside the timed region.
-        rows_d, heights_d, piece_d = env.export_boards()
-        h_rows = torch.empty(rows_d.shape, dtype=rows_d.dtype).pin_memory(); h_rows.copy_(rows_d)
-        h_piece = torch.empty(piece_d.shape, dtype=piece_d.dtype).pin_memory(); h_piece.copy_(piece_d)
-        h_heights = torch.empty(heights_d.shape, dtype=heights_d.dtype).pin_memory()
+        out["e2e"] = e2e
+        if e2e_serial is not None:
+            out["e2e_unpipelined"] = e2e_serial
         host_stats = torch.empty(len(_lib.STATS), dtype=torch.int64).pin_memory()
-        d_rows, d_piece = torch.empty_like(rows_d), torch.empty_like(piece_d)
-        h2d = h_rows.numel() * 2 + h_piece.numel() + 32
-        d2h = h_rows.numel() * 2 + h_heights.numel() + h_piece.numel() + 8 * len(_lib.STATS)
-
-        def e2e_step():
-            w_host = np.array(BCTS_WEIGHTS, np.float32)
-            d_rows.copy_(h_rows, non_blocking=True); d_piece.copy_(h_piece, non_blocking=True)
-            env.import_boards(d_rows, piece=d_piece)
-            env.rollout(T, "greedy", w_host)
-            r, hh, pp = env.export_boards()
-            h_rows.copy_(r, non_blocking=True); h_heights.copy_(hh, non_blocking=True); h_piece.copy_(pp, non_blocking=True)
-            host_stats.copy_(env.stats, non_blocking=True)
-            torch.cuda.synchronize()                                   # the caller reads the results
-        for _ in range(2):
-            e2e_step()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            e2e_step()
-        e2e_dt = time.perf_counter() - t0
-        out["e2e"] = {"value": E * T * K / e2e_dt, "unit": "placements/s", "h2d_bytes_per_step": h2d,
-                      "d2h_bytes_per_step": d2h,
-                      "note": "per step: boards + pieces of all envs H2D from pinned memory -> tb_import_boards -> "
-                              "tb_rollout (T placements per env) -> tb_export_boards -> boards, heights, pieces and "
-                              "statistics D2H; per rank"}
         # the same API with the games resident on the device (only weights in, statistics out)
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -458,3 +458,29 @@ def test_batched_fitness():
     for e in range(0, 500, 37):
         for k in range(9):
             assert s[e, k] == orc.fitness(f[e, k], orc.BCTS_WEIGHTS)
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 4])
+def test_host_rollout_equals_resident(chunks):
+    """HostRollout (host-resident boards, chunked over CUDA streams so copies overlap the rollout kernel) ends in the
+    same boards, pieces and statistics as the device-resident whole job, whatever the chunking, and its host
+    buffers agree with the oracle's replay of the same seeded games."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris, HostRollout
+    n, seed, T = 2051, 9, 25
+    whole = BatchedTetris(10, 10, n, piece_set=1, seed=seed)
+    host = HostRollout(10, 10, n, chunks=chunks, piece_set=1, seed=seed)
+    ob = orc.Batch(10, 10, n, piece_set=1, seed=seed)
+    ob.reset()
+    assert np.array_equal(host.h_piece.numpy(), whole.piece)
+    for policy, pid in (("random", 0), ("greedy", 1), ("greedy", 1)):
+        whole.rollout(T, policy)
+        ob.rollout(T, pid)
+        st = host.play(T, policy)
+        assert np.array_equal(host.h_rows.numpy().view(np.uint16), whole.rows())
+        assert np.array_equal(host.h_heights.numpy(), whole.heights)
+        assert np.array_equal(host.h_piece.numpy(), whole.piece)
+        assert np.array_equal(st.numpy(), whole.stats.cpu().numpy())
+        assert np.array_equal(host.h_rows.numpy().view(np.uint16), ob.rows())
+        assert np.array_equal(host.h_piece.numpy().astype(np.int32), np.asarray(ob.piece, np.int32))
+    assert int(st[1]) > 0                                  # episodes ended and were auto-reset on the way

@@ -19,6 +19,9 @@ def __getattr__(name):
     if name == "BatchedTetris":
         from .batched import BatchedTetris
         return BatchedTetris
+    if name == "HostRollout":
+        from .batched import HostRollout
+        return HostRollout
     if name == "Tetris":
         from .game import Tetris
         return Tetris

@@ -269,3 +269,68 @@ class BatchedTetris:
         """(num_rows+4, num_columns) int64 0/1 array of one env, the reference's State.representation."""
         rows = self.export_boards(env, 1)[0].cpu().numpy().view(np.uint16)[0]
         return ((rows[:, None] >> np.arange(self.num_columns, dtype=np.uint16)) & 1).astype(np.int64)
+
+
+class HostRollout:
+    """Games that live in HOST memory, played on the device (the cycle of a caller that keeps its boards on the host).
+
+    Every `play` copies the boards and pieces of all envs in from pinned host buffers (`h_rows` int16[n, R+4] row
+    masks, `h_piece` uint8[n]), imports them (tb_import_boards), plays `n_steps` placements per env with the fused
+    rollout kernel (tb_rollout), exports (tb_export_boards) and copies boards, heights and pieces back into the same
+    host buffers, plus the episode statistics.  The env range is cut into `chunks` contiguous shards -- each a
+    BatchedTetris with its global env_offset, on its own CUDA stream -- so the H2D copy of shard i+1 and the D2H copy
+    of shard i-1 overlap the rollout kernel of shard i.  Results do not depend on `chunks`: every env's piece stream
+    is keyed by its global env id (same argument as multi-GPU sharding).
+    """
+
+    def __init__(self, num_columns, num_rows, n_env, chunks=4, piece_set=1, seed=0, env_offset=0, device=None):
+        from .distributed import shard_range
+        self.n_env, self.chunks = int(n_env), max(1, min(int(chunks), int(n_env)))
+        self.bounds = []
+        self.envs = []
+        for i in range(self.chunks):
+            off, cnt = shard_range(self.n_env, i, self.chunks)
+            self.bounds.append((off, off + cnt))
+            self.envs.append(BatchedTetris(num_columns, num_rows, cnt, piece_set=piece_set, seed=seed,
+                                           env_offset=int(env_offset) + off, device=device))
+        e0 = self.envs[0]
+        self.device = e0.device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.envs]
+        self.h_rows = torch.zeros((self.n_env, e0.n_stored_rows), dtype=torch.int16).pin_memory()
+        self.h_heights = torch.zeros((self.n_env, e0.num_columns), dtype=torch.uint8).pin_memory()
+        self.h_piece = torch.zeros(self.n_env, dtype=torch.uint8).pin_memory()
+        self.h_stats = torch.zeros((self.chunks, len(_lib.STATS)), dtype=torch.int64).pin_memory()
+        self._d_rows = [torch.empty((b - a, e0.n_stored_rows), dtype=torch.int16, device=self.device) for a, b in self.bounds]
+        self._d_piece = [torch.empty(b - a, dtype=torch.uint8, device=self.device) for a, b in self.bounds]
+        self.h2d_bytes = self.h_rows.numel() * 2 + self.h_piece.numel() + 32          # + the 8 float32 weights
+        self.d2h_bytes = (self.h_rows.numel() * 2 + self.h_heights.numel() + self.h_piece.numel()
+                          + 8 * self.h_stats.numel())
+        self.pull()                                         # host buffers <- the freshly reset games
+
+    def pull(self):
+        """Host buffers <- device state (boards, heights, pieces), synchronously."""
+        for (a, b), env in zip(self.bounds, self.envs):
+            r, hh, pp = env.export_boards()
+            self.h_rows[a:b].copy_(r); self.h_heights[a:b].copy_(hh); self.h_piece[a:b].copy_(pp)
+
+    def play(self, n_steps, policy="greedy", weights=None):
+        """Host boards in -> n_steps placements per env -> host boards out.  Returns the combined cumulative episode
+        statistics (int64[len(STATS)], host).  Synchronous: the host buffers are valid on return."""
+        from .distributed import combine_stats
+        cur = torch.cuda.current_stream(self.device)
+        for i, (env, s) in enumerate(zip(self.envs, self.streams)):
+            a, b = self.bounds[i]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                self._d_rows[i].copy_(self.h_rows[a:b], non_blocking=True)
+                self._d_piece[i].copy_(self.h_piece[a:b], non_blocking=True)
+                env.import_boards(self._d_rows[i], piece=self._d_piece[i])
+                env.rollout(n_steps, policy, weights)
+                r, hh, pp = env.export_boards()
+                self.h_rows[a:b].copy_(r, non_blocking=True)
+                self.h_heights[a:b].copy_(hh, non_blocking=True)
+                self.h_piece[a:b].copy_(pp, non_blocking=True)
+                self.h_stats[i].copy_(env.stats, non_blocking=True)
+        for s in self.streams:
+            s.synchronize()
+        return combine_stats(list(self.h_stats))

@@ -1278,7 +1278,8 @@ int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_
     if (a_stride < 1) return fail("%s: a_stride must be >= the piece set's slot count", __func__);
     cudaStream_t st = (cudaStream_t)stream;
     const F8 dirs = f8_from(directions, 1.0f);
-    const int cfg = tuning_int("TB_K1_CFG", 0);
+    // small batches (fewer 256-env tiles than SMs) use 128-env tiles: twice the CTAs, half the per-tile latency
+    const int cfg = tuning_int("TB_K1_CFG", (n_env + 255) / 256 < sm_count() ? 3 : 0);
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
         typedef void (*kern_t)(StateView, float *, unsigned long long *, int *, int, F8, int);           \
@@ -1357,7 +1358,7 @@ static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_of
         else {                                                                                           \
             typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int);          \
             kern_t kern; size_t smem; int tile, minb;                                                    \
-            const int k3cfg = tuning_int("TB_K3_CFG", 0);                                                \
+            const int k3cfg = tuning_int("TB_K3_CFG", (n_env + 255) / 256 < sm_count() ? 2 : 0);         \
             if (k3cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<c, r, 128, 5>;          \
                 smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
             else if (k3cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<c, r, 128, 4>;          \
