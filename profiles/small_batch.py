@@ -9,7 +9,7 @@ CHILD = r'''
 import os, sys, json, torch
 from tetris_b200 import BatchedTetris
 res = {}
-for n in (4096, 16384, 32768, 65536):
+for n in (1024, 4096, 8192, 16384, 32768, 65536):
     env = BatchedTetris(10, 20, n, piece_set=1, seed=0x5EED)
     env.rollout(30, "random"); env.rollout(32, "greedy")
     f = torch.empty((n, env.a_max, 8), dtype=torch.float32, device="cuda"); v = torch.empty(n, dtype=torch.int64, device="cuda"); c = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -28,7 +28,7 @@ print(json.dumps(res))
 '''
 out = {}
 for name, envs in (("default", {}), ("cfg0", {"TB_K1_CFG": "0", "TB_K3_CFG": "0"}), ("k1cfg3_k3cfg2", {"TB_K1_CFG": "3", "TB_K3_CFG": "2"}),
-                   ("k1cfg3_k3cfg3", {"TB_K1_CFG": "3", "TB_K3_CFG": "3"})):
+                   ("cfg4_32x128", {"TB_K1_CFG": "4", "TB_K3_CFG": "4"}), ("cfg5_64x256", {"TB_K1_CFG": "5", "TB_K3_CFG": "5"})):
     e = dict(os.environ); e.update(envs)
     r = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out[name] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else r.stderr[-400:]

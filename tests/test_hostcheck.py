@@ -65,6 +65,23 @@ def random_board(rng, Cc, R, fill):
     return rep
 
 
+def tall_dense_board(rng, Cc, R):
+    """Dense stack reaching the top rows but for a 1-4 column gap: the top rows are near-full, so placements that poke
+    above row R are legal exactly when they complete enough of them (the rescue path of valid_slots)."""
+    rep = np.zeros((R + 4, Cc), np.uint8)
+    top = int(rng.integers(max(R - 4, 1), R + 1))
+    rep[:top] = 1
+    gw = int(rng.integers(1, min(4, Cc - 1) + 1))
+    g0 = int(rng.integers(0, Cc - gw + 1))
+    for c in range(g0, g0 + gw):
+        rep[int(rng.integers(max(top - 5, 0), top)):, c] = 0
+    for _ in range(int(rng.integers(0, 4))):                 # a few holes below the surface (never a full row: the gap)
+        r, c = int(rng.integers(0, top)), int(rng.integers(0, Cc))
+        if rep[r + 1:, c].any():
+            rep[r, c] = 0
+    return rep
+
+
 def played_boards(Cc, R, n_env, steps, seed):
     b = orc.Batch(Cc, R, n_env, piece_set=1, seed=seed)
     b.reset()
@@ -101,6 +118,7 @@ def test_core_vs_oracle(hc, shape):
     for fill in (0.4, 0.7, 0.9, 0.97, 1.0):
         boards += [random_board(rng, Cc, R, fill) for _ in range(40)]
     boards += list(played_boards(Cc, R, 24, 12, seed=5))
+    boards += [tall_dense_board(rng, Cc, R) for _ in range(120)]
     for rep in boards:
         check_board(hc, Cc, R, rep, stats)
     assert stats[0] > 5000

@@ -472,9 +472,9 @@ TB_HD uint16_t run_tab_entry(uint32_t m)
 {
     constexpr int HB = RunTab<R>::HB;
     const int rs = run_sum(m);
-    int trail = 0, lead = 0;
-    while (trail < HB && ((m >> trail) & 1u)) ++trail;
-    while (lead < HB && ((m >> (HB - 1 - lead)) & 1u)) ++lead;
+    const uint32_t z = ~m & mask_lo(HB);                           // the zero bits of the half
+    const int trail = z ? ctz32(z) : HB;                           // ones below the lowest zero
+    const int lead = z ? clz32(z) - (32 - HB) : HB;                // ones above the highest zero
     return (uint16_t)(rs | (trail << 8) | (lead << 12));
 }
 template <int R>
@@ -797,6 +797,16 @@ TB_HD bool placement_valid(const uint32_t *col, uint32_t d, int c, int hmax)
 // (`nearfull`, a bit-sliced count of the empty cells of every row) -- only then is the exact test run.
 // `ori` = the orientation table (shared memory on the device).  Precondition: every column height <= R.
 // ANY_ONLY: return non-zero as soon as one legal slot is found (the mask is then not complete).
+// insert a zero above every one of the low 16 bits
+TB_HD uint32_t spread16(uint32_t x)
+{
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
 template <int C, int R, bool ANY_ONLY = false>
 TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uint32_t *ori)
 {
@@ -808,6 +818,78 @@ TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uin
     for (int k = 0; k < C; ++k) any |= col[k];
     const int hmax = height_of(any);
     if (hmax + 4 <= R) return (1ull << total) - 1ull;   // every piece is at most 4 rows tall
+    if (C > 4) {
+        // Tall board, all columns at once.  A placement that stays at or below row R is legal.  One that pokes above R
+        // (anchor a >= R - 3) is legal only if it completes enough rows among a .. R-1 (rows >= R are empty).  With
+        // G_k = {columns taller than R - 4 + k} as a bit mask, "top <= R" <=> every piece column dx has
+        // h[c + dx] <= R - ph + bot[dx] = R - 4 + k (k = 4 - ph + bot is always in 0..3), so the anchor columns that poke
+        // above R are OR_dx (G_k(dx) >> dx): no loop over slots.  A poking placement can only be rescued by completing a
+        // row r in R-3 .. R-1 that has at most 4 empty cells, all of them under the piece: its anchor column then lies in
+        // [hi_r - w + 1, lo_r] (lo_r / hi_r = first / last empty cell of the row) -- only those few get the exact test.
+        // The top four legal rows, as row masks, come from the columns by a 4 x C bit gather.
+        // (bit j of a column's top nibble -> bit 0 of byte j by one multiply; columns 0-7 and 8-9 in two accumulators)
+        uint32_t acc0 = 0u, acc1 = 0u;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const uint32_t x = ((col[k] >> (R - 4)) * 0x00204081u) & 0x01010101u;   // heights are <= R: at most 4 bits
+            if (k < 8) acc0 |= x << k; else acc1 |= x << (k - 8);
+        }
+        uint32_t row[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[j] = ((acc0 >> (8 * j)) & 0xFFu) | (((acc1 >> (8 * j)) & 0xFFu) << 8);
+        const uint32_t g3 = row[3], g2 = g3 | row[2], g1 = g2 | row[1], g0 = g1 | row[0];
+        const uint64_t gg = (uint64_t)g0 | (uint64_t)g1 << 16 | (uint64_t)g2 << 32 | (uint64_t)g3 << 48;
+        // near-full rows among R-3 .. R-1: span of their empty cells, lo | hi << 8 | 1 << 16 (0 = not near-full)
+        uint32_t span[3];
+        uint32_t near = 0u;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const uint32_t e = ~row[j + 1] & S::FULLROW;
+            span[j] = (popc32(e) <= 4 && e != 0u) ? ((uint32_t)ctz32(e) | (uint32_t)(31 - clz32(e)) << 8 | 1u << 16) : 0u;
+            near |= span[j];
+        }
+        unsigned long long m = 0ull, cs = 0ull;                // legal slots; poking slots that need the exact test
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {                          // rolled on purpose: instruction footprint
+            const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase;
+            const int sbase = l ? n0 * (C - w0 + 1) : 0;
+            const uint32_t range = mask_lo(C - w + 1);
+            uint32_t rescue = 0u;                              // anchor columns whose piece covers a near-full row's gap
+            if (near != 0u) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int lo = (int)(span[j] & 0xFFu), hi = (int)((span[j] >> 8) & 0xFFu);
+                    if (span[j] != 0u && hi - lo < w) rescue |= mask_lo(lo + 1) & ~mask_lo(imax(hi - w + 1, 0));
+                }
+            }
+#pragma unroll 1
+            for (int o = 0; o < n; ++o) {
+                const uint32_t d = ori[ob + o];
+                const int ph = desc_ph(d);
+                uint32_t bad = 0u;
+#pragma unroll
+                for (int dx = 0; dx < 4; ++dx)
+                    if (dx < w) bad |= ((uint32_t)(gg >> (16 * (4 - ph + desc_bot(d, dx)))) & 0xFFFFu) >> dx;
+                const uint32_t ok = ~bad & range, cd = bad & rescue & range;
+                // loop-local slot of (column c, orientation o) = c * n + o
+                m |= (unsigned long long)(n == 2 ? spread16(ok) << o : ok) << sbase;
+                cs |= (unsigned long long)(n == 2 ? spread16(cd) << o : cd) << sbase;
+            }
+        }
+        if (ANY_ONLY && m != 0ull) return 1ull;
+        while (cs != 0ull) {                                   // rare: the one copy of the exact test
+            const uint32_t lo32 = (uint32_t)cs;
+            const int slot = lo32 ? ctz32(lo32) : 32 + ctz32((uint32_t)(cs >> 32));
+            cs &= cs - 1ull;
+            int oi, c;
+            slot_to_placement(pw, C, slot, oi, c);
+            if (placement_valid<C, R>(col, ori[oi], c, hmax)) {
+                if (ANY_ONLY) return 1ull;
+                m |= 1ull << slot;
+            }
+        }
+        return m;
+    }
     uint64_t hp = 0;                                    // heights, 5 bits per column
     uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;            // bit-sliced count of empty cells per row
 #pragma unroll

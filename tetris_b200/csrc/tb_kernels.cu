@@ -199,9 +199,9 @@ struct CtaSmem {
 };
 // K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements,
 // and per-warp episode statistics
-template <int TILE> struct BestSmem {
+template <int TILE, int THREADS = TILE> struct BestSmem {
     unsigned long long best[TILE];
-    long long wstat[TILE / 32][TB_ST_COUNT];
+    long long wstat[THREADS / 32][TB_ST_COUNT];
     uint8_t bslot[TILE][2];              // slot of the best score per column loop
 };
 
@@ -234,8 +234,9 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
 // (m0, m1: column loops 0 / 1, bit 16 * o + c).  The set bits of all 32 envs are flattened over the lanes, 32 items per
 // pass, so the general evaluation runs with full warps however the items are spread over the envs.
 // f(owner lane, loop l, orientation o in the loop, column c) is called for every item by one lane.
+// With several warps per 32-env group (small-batch configurations) warp `sub` of `nsub` takes every nsub-th pass.
 template <typename F>
-__device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int lane, F &&f)
+__device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int lane, int sub, int nsub, F &&f)
 {
     const int cnt = __popc(m0) + __popc(m1);
     int incl = cnt;
@@ -245,7 +246,7 @@ __device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int
         if (lane >= d) incl += v;
     }
     const int total = __shfl_sync(FULLMASK, incl, 31);
-    for (int base = 0; base < total; base += 32) {
+    for (int base = 32 * sub; base < total; base += 32 * nsub) {
         const int i = base + lane;
         int owner = 0;                                     // first lane whose inclusive prefix exceeds i
 #pragma unroll
@@ -265,15 +266,6 @@ __device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int
     }
 }
 
-// insert a zero above every one of the low 16 bits
-__device__ __forceinline__ uint32_t spread16(uint32_t x)
-{
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x;
-}
 // legal columns per orientation (16 bits each, orientation-major) -> loop-local slot bits c * n + o
 __device__ __forceinline__ uint32_t slots_of(uint32_t v, int n)
 {
@@ -299,17 +291,23 @@ __device__ __forceinline__ float *feat_row(float *__restrict__ feats, int64_t en
 
 template <int V> struct IntC { static constexpr int value = V; };
 
-template <int C, int R, bool DIRS, int TILE>
+// THREADS = CTA size, a multiple of TILE.  THREADS == TILE is the throughput configuration (thread per env in the
+// per-env phases, warp w owns envs 32w .. 32w+31).  THREADS > TILE is the small-batch configuration: the per-env phases
+// use the first TILE threads, phase B spreads the windows over all warps and WPG = THREADS / TILE warps share the
+// phase-S items of each 32-env group, which shortens the critical path of a tile when there are fewer tiles than SMs.
+template <int C, int R, bool DIRS, int TILE, int THREADS>
 __device__ __forceinline__ void
 afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
                  int *__restrict__ count_out, int a_stride, const F8 &dirs, int flags)
 {
     using K = Env<C, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NWARPS = TILE / 32;
+    static_assert(TILE % 32 == 0 && THREADS % TILE == 0, "TILE: whole warps of envs; THREADS: a multiple of TILE");
+    constexpr int NWARPS = THREADS / 32, NGROUPS = TILE / 32, WPG = NWARPS / NGROUPS;
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
     stage_cta(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool env_thread = THREADS == TILE || tid < TILE;   // this thread owns env `tid` of the tile in the per-env phases
     const bool want_terminal = (flags & TB_FLAG_INCLUDE_TERMINAL) != 0;
     const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
     int par = 0;
@@ -318,9 +316,11 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
         const int64_t e0 = tile * TILE, e = e0 + tid;
         int *cnt = sm.cnt[par];
         // ---- phase A (thread per env).  cnt[par] was zeroed during the previous tile's phase B.
-        sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
-        sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
-        if (e < sv.n_env) {
+        if (env_thread) {
+            sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
+            sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
+        }
+        if (env_thread && e < sv.n_env) {
             uint32_t col[C];
             load_board<C, R>(sv, e, col);
             const Meta mt = unpack_meta(sv.meta[e]);
@@ -383,9 +383,12 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
         }
         __syncthreads();                                   // every warp is done with phase B: vloc / sloc are complete
         // ---- phase S: the placements that need the general evaluation (they clear a line), of this warp's own 32 envs,
-        // one lane per item.  Only warp-local data from here to the next tile's phase A: no further CTA barrier.
-        for_each_slow_item(sm.sloc[tid][0], sm.sloc[tid][1], lane, [&](int owner, int l, int o, int cc) {
-            const int env = (warp << 5) + owner;
+        // one lane per item.  Only warp-local data from here to the next tile's phase A: no further CTA barrier
+        // (THREADS == TILE; with WPG warps per group the tile ends with a barrier instead).
+        const int grp = WPG == 1 ? warp : warp % NGROUPS, sub = WPG == 1 ? 0 : warp / NGROUPS;
+        for_each_slow_item(sm.sloc[(grp << 5) + lane][0], sm.sloc[(grp << 5) + lane][1], lane, sub, WPG,
+                           [&](int owner, int l, int o, int cc) {
+            const int env = (grp << 5) + owner;
             const uint32_t pw = sm.piece[sm.pid[env]];
             const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
             const int slot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
@@ -395,7 +398,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
         });
         __syncwarp();
         // ---- legal-action masks, thread per env (coalesced)
-        if (e < sv.n_env) {
+        if (env_thread && e < sv.n_env) {
             const uint32_t pw = sm.piece[sm.pid[tid]];
             const int n0 = (int)(pw & 3u), n1 = (int)((pw >> 5) & 3u);
             const int s1 = n0 * (C - (int)((pw >> 2) & 7u) + 1);
@@ -404,15 +407,16 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             if (valid_out) valid_out[e] = v;
             if (count_out) count_out[e] = __popcll(v);
         }
+        if (WPG > 1) __syncthreads();                      // the other warps of a group may still read its records / masks
     }
 }
 
-template <int C, int R, bool DIRS, int TILE, int MINB>
-__global__ void __launch_bounds__(TILE, MINB)
+template <int C, int R, bool DIRS, int TILE, int MINB, int THREADS = TILE>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
               int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
 {
-    afterstates_body<C, R, DIRS, TILE>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
+    afterstates_body<C, R, DIRS, TILE, THREADS>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
 }
 // Afterstates with boards (compat layer / small batches): one thread per (env, slot), general path.
 template <int C, int R>
@@ -677,27 +681,31 @@ __device__ __forceinline__ unsigned long long score_key(uint32_t ord, int slot)
 // keep the first arg-max per env and column loop, S (per warp) its line-clearing placements, C (thread per env) apply
 // the chosen placement.  Between steps the board lives in the record's column words, not in registers: only the
 // bag / counters stay in registers across phase B.  Episode statistics are aggregated per warp in shared memory.
-template <int C, int R, int TILE, int MINB>
-__global__ void __launch_bounds__(TILE, MINB)
+// THREADS > TILE: small-batch configuration, see afterstates_body.
+template <int C, int R, int TILE, int MINB, int THREADS = TILE>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats,
                  int no_reset)
 {
     using K = Env<C, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NWARPS = TILE / 32;
+    static_assert(TILE % 32 == 0 && THREADS % TILE == 0, "TILE: whole warps of envs; THREADS: a multiple of TILE");
+    constexpr int NWARPS = THREADS / 32, NGROUPS = TILE / 32, WPG = NWARPS / NGROUPS;
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
-    BestSmem<TILE> &bs = *reinterpret_cast<BestSmem<TILE> *>(smem_raw + ((sizeof(CtaSmem<C, R, TILE>) + 15) & ~(size_t)15));
+    BestSmem<TILE, THREADS> &bs =
+        *reinterpret_cast<BestSmem<TILE, THREADS> *>(smem_raw + ((sizeof(CtaSmem<C, R, TILE>) + 15) & ~(size_t)15));
     stage_cta(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool env_thread = THREADS == TILE || tid < TILE;   // this thread owns env `tid` of the tile in the per-env phases
     const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
     long long *wstat = bs.wstat[warp];
     if (lane < TB_ST_COUNT) wstat[lane] = 0;
     int par = 0;
-    uint32_t *myrec = sm.rec + tid * K::WORDS;
+    uint32_t *myrec = sm.rec + (env_thread ? tid : 0) * K::WORDS;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t e = tile * TILE + tid;
-        const bool in_range = e < sv.n_env;
+        const bool in_range = env_thread && e < sv.n_env;
         bool active = in_range;                            // false once finished in a no-reset rollout
         Meta mt; mt.piece = 0; mt.bag = 0u; mt.draws = 0u;
         uint2 ep = make_uint2(0u, 0u);
@@ -712,15 +720,19 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
 #pragma unroll
                 for (int i = 0; i < C; ++i) col[i] = 0u;
             }
+            if (env_thread) {
 #pragma unroll
-            for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
+                for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
+            }
         }
         for (int t = 0; t < n_steps; ++t, par ^= 1) {
             int *cnt = sm.cnt[par];
             // ---- phase A (thread per env).  cnt[par] was zeroed during the previous step's phase B.
-            sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
-            sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
-            bs.best[tid] = 0ull;
+            if (env_thread) {
+                sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
+                sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
+                bs.best[tid] = 0ull;
+            }
             int n_slots = 0;
             if (active) {
                 build_env<C, R>(sm.run, myrec);         // the columns are already in the record
@@ -794,8 +806,10 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             }
             __syncthreads();                               // phase B is complete: vloc / bslot / sloc of every env
             // ---- phase S: the line-clearing legal placements of this warp's own 32 envs, one lane per item
-            for_each_slow_item(sm.sloc[tid][0], sm.sloc[tid][1], lane, [&](int owner, int l, int o, int cc) {
-                const int env = (warp << 5) + owner;
+            const int grp = WPG == 1 ? warp : warp % NGROUPS, sub = WPG == 1 ? 0 : warp / NGROUPS;
+            for_each_slow_item(sm.sloc[(grp << 5) + lane][0], sm.sloc[(grp << 5) + lane][1], lane, sub, WPG,
+                               [&](int owner, int l, int o, int cc) {
+                const int env = (grp << 5) + owner;
                 const uint32_t pw = sm.piece[sm.pid[env]];
                 const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
                 const int slot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
@@ -803,7 +817,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
                 atomicMax(&bs.best[env], score_key(orderable(fitness(ev.f, wts.v)), slot));
             });
-            __syncwarp();                                  // phase C reads the best keys of this warp's envs only
+            if (WPG == 1) __syncwarp();                    // phase C reads the best keys of this warp's envs only
+            else __syncthreads();                          // ... or of a group that several warps worked on
             // ---- phase C (thread per env): apply the choice, draw the next piece, game over / auto-reset
             int lc = 0;
             bool placed = false, dn = false;
@@ -1162,6 +1177,7 @@ static int sm_count()
 // Tuning knobs read from the environment (experiments only; the defaults are what ships and what is tested):
 //   TB_K1_CFG  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5
 //   TB_K3_CFG  0: 256 x 2 (default)   2: 128 x 4   3: 128 x 5
+//   both       4: 32 envs x 128 threads   5: 64 envs x 256 threads   (several warps per 32-env group, small batches)
 static int tuning_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -1182,6 +1198,15 @@ static unsigned grid_for(int64_t work_items, int per_block, int blocks_per_sm)
     const int64_t need = (work_items + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * blocks_per_sm;         // persistent: a multiple of the SM count
     return (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+// Tile configuration by batch size: the throughput configuration (cfg 0, 256-env tiles, thread per env) once there is
+// at least one tile per SM; below that 128-env tiles (`mid`); and for batches of at most TB_SMALL_GROUPS (default 4)
+// 32-env groups per SM the small-batch configuration 4 (32 envs and 4 warps per CTA: shortest critical path).
+static int small_batch_cfg(int64_t n_env, int mid)
+{
+    const int sms = sm_count();
+    if ((n_env + 31) / 32 <= (int64_t)tuning_int("TB_SMALL_GROUPS", 4) * sms) return 4;
+    return (n_env + 255) / 256 < sms ? mid : 0;
 }
 static F8 f8_from(const float *p, float dflt)
 {
@@ -1279,19 +1304,23 @@ int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_
     cudaStream_t st = (cudaStream_t)stream;
     const F8 dirs = f8_from(directions, 1.0f);
     // small batches (fewer 256-env tiles than SMs) use 128-env tiles: twice the CTAs, half the per-tile latency
-    const int cfg = tuning_int("TB_K1_CFG", (n_env + 255) / 256 < sm_count() ? 3 : 0);
+    const int cfg = tuning_int("TB_K1_CFG", small_batch_cfg(n_env, 3));
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
         typedef void (*kern_t)(StateView, float *, unsigned long long *, int *, int, F8, int);           \
-        kern_t kern; size_t smem; int tile, minb;                                                        \
-        if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<c, r, 128>);                    \
+        kern_t kern; size_t smem; int tile, minb, threads = 0;                                           \
+        if (cfg == 4) { tile = 32; threads = 128; minb = 4; smem = sizeof(CtaSmem<c, r, 32>);            \
+            kern = directions ? k_afterstates<c, r, true, 32, 4, 128> : k_afterstates<c, r, false, 32, 4, 128>; }\
+        else if (cfg == 5) { tile = 64; threads = 256; minb = 2; smem = sizeof(CtaSmem<c, r, 64>);       \
+            kern = directions ? k_afterstates<c, r, true, 64, 2, 256> : k_afterstates<c, r, false, 64, 2, 256>; }\
+        else if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<c, r, 128>);                    \
             kern = directions ? k_afterstates<c, r, true, 128, 5> : k_afterstates<c, r, false, 128, 5>; }\
         else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<c, r, 256>);                    \
             kern = directions ? k_afterstates<c, r, true, 256, 2> : k_afterstates<c, r, false, 256, 2>; }\
         else { tile = 256; minb = 3; smem = sizeof(CtaSmem<c, r, 256>);                                  \
             kern = directions ? k_afterstates<c, r, true, 256, 3> : k_afterstates<c, r, false, 256, 3>; }\
         if (opt_in_smem((const void *)kern, smem)) return -2;                                            \
-        kern<<<grid_for(n_env, tile, minb), tile, smem, st>>>(make_view<c, r>(state, n_env), feats_out,  \
+        kern<<<grid_for(n_env, tile, minb), threads ? threads : tile, smem, st>>>(make_view<c, r>(state, n_env), feats_out,  \
             (unsigned long long *)valid_out, count_out, a_stride, dirs, flags);                          \
         return check_launch("tb_afterstates");                                                           \
     }
@@ -1357,16 +1386,20 @@ static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_of
                 env_offset, seed, piece_set, n_steps, stats, no_reset);                                  \
         else {                                                                                           \
             typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int);          \
-            kern_t kern; size_t smem; int tile, minb;                                                    \
-            const int k3cfg = tuning_int("TB_K3_CFG", (n_env + 255) / 256 < sm_count() ? 2 : 0);         \
-            if (k3cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<c, r, 128, 5>;          \
+            kern_t kern; size_t smem; int tile, minb, threads = 0;                                       \
+            const int k3cfg = tuning_int("TB_K3_CFG", small_batch_cfg(n_env, 2));                        \
+            if (k3cfg == 4) { tile = 32; threads = 128; minb = 4; kern = k_rollout_greedy<c, r, 32, 4, 128>; \
+                smem = ((sizeof(CtaSmem<c, r, 32>) + 15) & ~(size_t)15) + sizeof(BestSmem<32, 128>); }   \
+            else if (k3cfg == 5) { tile = 64; threads = 256; minb = 2; kern = k_rollout_greedy<c, r, 64, 2, 256>; \
+                smem = ((sizeof(CtaSmem<c, r, 64>) + 15) & ~(size_t)15) + sizeof(BestSmem<64, 256>); }   \
+            else if (k3cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<c, r, 128, 5>;          \
                 smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
             else if (k3cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<c, r, 128, 4>;          \
                 smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
             else { tile = 256; minb = 2; kern = k_rollout_greedy<c, r, 256, 2>;                          \
                 smem = ((sizeof(CtaSmem<c, r, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }      \
             if (opt_in_smem((const void *)kern, smem)) return -2;                                        \
-            kern<<<grid_for(n_env, tile, minb), tile, smem, st>>>(                                       \
+            kern<<<grid_for(n_env, tile, minb), threads ? threads : tile, smem, st>>>(                   \
                 make_view<c, r>(state, n_env), env_offset, seed, piece_set, n_steps, wts, stats, no_reset); \
         }                                                                                                \
         return check_launch("tb_rollout");                                                               \
