@@ -484,3 +484,30 @@ def test_host_rollout_equals_resident(chunks):
         assert np.array_equal(host.h_rows.numpy().view(np.uint16), ob.rows())
         assert np.array_equal(host.h_piece.numpy().astype(np.int32), np.asarray(ob.piece, np.int32))
     assert int(st[1]) > 0                                  # episodes ended and were auto-reset on the way
+
+
+@pytest.mark.parametrize("k1cfg,k3cfg", [(0, 0), (2, 0), (3, 2), (3, 3), (4, 4), (5, 5)])
+def test_tile_configurations(k1cfg, k3cfg, monkeypatch):
+    """tb_afterstates / tb_rollout pick a CTA tile configuration by batch size (throughput: 256-env tiles; small
+    batches: 128-env tiles, or 32 / 64 envs with several warps per env group).  Every configuration must give the
+    oracle's results: forced here through the library's tuning variables on a batch with ragged tiles, on a board where
+    line clears and game overs are frequent and on the headline board."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    monkeypatch.setenv("TB_K1_CFG", str(k1cfg))
+    monkeypatch.setenv("TB_K3_CFG", str(k3cfg))
+    for (Cc, R, n, T) in ((6, 12, 1337, 40), (10, 20, 777, 60)):
+        env = BatchedTetris(Cc, R, n, piece_set=1, seed=77)
+        ob = orc.Batch(Cc, R, n, piece_set=1, seed=77)
+        ob.reset()
+        env.rollout(25, "random"); s0 = ob.rollout(25, 0, threads=8)
+        env.rollout(T, "greedy"); s1 = ob.rollout(T, 1, threads=8)
+        _compare_state(env, ob)
+        total = s0 + s1
+        total[10:12] = np.maximum(s0[10:12], s1[10:12])    # the two maxima combine by max, the rest by sum
+        assert np.array_equal(env.stats.cpu().numpy(), total)
+        feats, valid, count = env.get_after_states(include_terminal=True)
+        of, ov, oc, on = ob.afterstates()
+        mask = np.arange(env.a_max)[None, :] < on[:, None]
+        assert np.array_equal(feats.cpu().numpy()[mask], of[mask])
+        assert np.array_equal(valid.cpu().numpy().view(np.uint64), ov) and np.array_equal(count.cpu().numpy(), oc)
