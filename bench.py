@@ -443,6 +443,13 @@ def run_ours(args):
                 replay()
             torch.cuda.synchronize()
             out["lockstep_4096_cuda_graph_placements_per_s"] = 4096 * 200 / (time.perf_counter() - t0)
+            # the same 4096 envs with the policy inside the kernel (fused rollouts, small-batch tile configuration)
+            for pol in ("random", "greedy"):
+                envg.rollout(64, pol)
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); envg.rollout(256, pol); e.record(); torch.cuda.synchronize()
+                out["fused_4096_%s_placements_per_s" % pol] = 4096 * 256 / (s.elapsed_time(e) * 1e-3)
         except Exception as ex:
             out["random_policy_placements_per_s_per_gpu"] = repr(ex)
 
