@@ -171,7 +171,8 @@ k_reset(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const ui
 // ---------------------------------------------------------------------------------------------
 // K1 afterstates.
 //
-// A CTA owns a tile of TILE envs (= its thread count, a template parameter; 224 or 256).  Phase A (thread per env): load + transpose the board, build the env
+// A CTA owns a tile of TILE envs (template parameter; THREADS = TILE threads in the throughput configuration, a multiple
+// of TILE in the small-batch ones).  Phase A (thread per env): load + transpose the board, build the env
 // record in shared memory, append the env to the list of its piece.  Phase B (warp per window): all lanes of a
 // warp work on envs holding the SAME piece -- lane = (env k of the window, anchor column c) -- and walk the piece's
 // orientations in a warp-uniform loop, so the orientation descriptor is uniform, every loop over the piece's
