@@ -139,3 +139,6 @@ def test_no_cpu_fallback():
     from tetris_b200 import BatchedTetris
     with pytest.raises(RuntimeError, match="no CUDA device"):
         BatchedTetris(10, 20, 8)
+    from tetris_b200 import HostRollout
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        HostRollout(10, 20, 64, chunks=2)
