@@ -211,7 +211,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("TB_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("TB_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")              # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     K, W, T, E = args.steps, args.warmup, args.rollout_steps, args.envs
     W = max(W, 3)
