@@ -6,6 +6,7 @@ current piece's placements in the reference's action order, `step(a)` takes the 
 (`reset_masked`) or in place (`auto_reset=True`, what example_play.py:20-21 does).
 All compute runs in the CUDA kernels of csrc/tb_kernels.cu; torch only owns memory and streams.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -33,9 +34,10 @@ class BatchedTetris:
             raise ValueError("board shape %dx%d is not compiled in (see TB_SHAPES in csrc/tb_kernels.cu)"
                              % (self.num_columns, self.num_rows))
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.a_max = L.tb_a_max(self.num_columns, self.piece_set)
         self.n_stored_rows = self.num_rows + 4
-        with torch.cuda.device(self.device):
+        with self._on_device():
             self.state = torch.zeros(L.tb_state_bytes(self.num_columns, self.num_rows, self.n_env),
                                      dtype=torch.uint8, device=self.device)
             self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -44,6 +46,12 @@ class BatchedTetris:
         self.reset()
 
     # -- plumbing ---------------------------------------------------------------------------
+    def _on_device(self):
+        """Context that makes self.device current; free when it already is (the common single-GPU-per-process case)."""
+        if torch.cuda.current_device() == self._dev_index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -70,14 +78,14 @@ class BatchedTetris:
     def reset(self, tape=None):
         """Tetris.__init__ + reset for every env (game.py:21-63).  tape: uint8[n_env] first pieces (global ids)."""
         t = self._dev_u8(tape)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
                                            _ptr(t), None, self._stream()))
 
     def reset_masked(self, mask, tape=None):
         """Tetris.reset() (game.py:53-63) on the envs where mask is set: board emptied, one more piece drawn."""
         m, t = self._dev_u8(mask), self._dev_u8(tape)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
                                            _ptr(t), _ptr(m), self._stream()))
 
@@ -96,7 +104,7 @@ class BatchedTetris:
         else:
             feats, valid, count = out
         d = None if self._dirs is None else self._dirs.ctypes.data_as(C.c_void_p)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_afterstates(*self._common(), _ptr(feats), _ptr(valid), _ptr(count),
                                                  self.a_max, d,
                                                  _lib.FLAG_INCLUDE_TERMINAL if include_terminal else 0,
@@ -117,7 +125,7 @@ class BatchedTetris:
         done = torch.empty(self.n_env, dtype=torch.uint8, device=self.device)
         lines = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
         flags = (_lib.FLAG_AUTO_RESET if auto_reset else 0) | (_lib.FLAG_ACTION_IS_SLOT if action_is_slot else 0)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             if check:
                 self._status.zero_()
             _lib.check(_lib.lib().tb_step(*self._common(), self.env_offset, self.seed, self.piece_set, _ptr(a), _ptr(t),
@@ -134,7 +142,7 @@ class BatchedTetris:
         pol = {"random": _lib.POLICY_RANDOM, "greedy": _lib.POLICY_GREEDY, 0: 0, 1: 1}[policy]
         w = np.ascontiguousarray(BCTS_WEIGHTS if weights is None else weights, dtype=np.float32)
         assert w.shape == (8,)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_rollout(*self._common(), self.env_offset, self.seed, self.piece_set, int(n_steps),
                                              pol, w.ctypes.data_as(C.c_void_p), _ptr(self.stats), self._stream()))
         return self.stats
@@ -153,7 +161,7 @@ class BatchedTetris:
         seed2 = (self.seed ^ 0xF02C) if seed is None else int(seed) & (2 ** 64 - 1)
         L = _lib.lib()
         n_child = self.n_env * self.a_max * int(n)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             child = torch.empty(L.tb_state_bytes(self.num_columns, self.num_rows, n_child), dtype=torch.uint8,
                                 device=self.device)
             ret = torch.empty((self.n_env, self.a_max), dtype=torch.int32, device=self.device)
@@ -176,7 +184,7 @@ class BatchedTetris:
         if actions is not None:
             a = actions.to(device=self.device, dtype=torch.int32).contiguous()
             grad = torch.empty((self.n_env, 8), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_action_probabilities(self.n_env, self.a_max, _ptr(feats.contiguous()), _ptr(valid),
                                                           w.ctypes.data_as(C.c_void_p), float(temperature), _ptr(a),
                                                           _ptr(probs), _ptr(grad), self._stream()))
@@ -188,7 +196,7 @@ class BatchedTetris:
         w = np.ascontiguousarray(BCTS_WEIGHTS if weights is None else weights, dtype=np.float32)
         f = feats.contiguous()
         out = torch.empty(f.shape[:-1], dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_fitness(out.numel(), _ptr(f), w.ctypes.data_as(C.c_void_p), _ptr(out), self._stream()))
         return out
 
@@ -200,7 +208,7 @@ class BatchedTetris:
         for small batches the iteration is launch-bound, this removes the per-kernel launch cost -- and `outputs` is
         the dict of static tensors it fills (feats, valid, count, actions, obs, reward, done, lines)."""
         out = {}
-        with torch.cuda.device(self.device):
+        with self._on_device():
             feats = torch.empty((self.n_env, self.a_max, 8), dtype=torch.float32, device=self.device)
             valid = torch.empty(self.n_env, dtype=torch.int64, device=self.device)
             count = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
@@ -234,7 +242,7 @@ class BatchedTetris:
         rows = torch.empty((count, self.n_stored_rows), dtype=torch.int16, device=self.device)
         heights = torch.empty((count, self.num_columns), dtype=torch.uint8, device=self.device)
         piece = torch.empty(count, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_export_boards(*self._common(), first, count, _ptr(rows), _ptr(heights), _ptr(piece),
                                                    self._stream()))
         return rows, heights, piece
@@ -250,7 +258,7 @@ class BatchedTetris:
         if r.dim() != 2 or r.shape[1] != self.n_stored_rows:
             raise ValueError("rows must have shape (count, num_rows + 4)")
         p = self._dev_u8(piece)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             _lib.check(_lib.lib().tb_import_boards(*self._common(), first, r.shape[0], _ptr(r), _ptr(p), self._stream()))
 
     # numpy conveniences (host copies)

@@ -840,13 +840,14 @@ TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uin
         const uint32_t g3 = row[3], g2 = g3 | row[2], g1 = g2 | row[1], g0 = g1 | row[0];
         const uint64_t gg = (uint64_t)g0 | (uint64_t)g1 << 16 | (uint64_t)g2 << 32 | (uint64_t)g3 << 48;
         // near-full rows among R-3 .. R-1: span of their empty cells, lo | hi << 8 | 1 << 16 (0 = not near-full)
-        uint32_t span[3];
-        uint32_t near = 0u;
+        uint32_t span[3] = {0u, 0u, 0u};
+        const bool near = popc32(row[1]) >= C - 4 || popc32(row[2]) >= C - 4 || popc32(row[3]) >= C - 4;
+        if (near) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const uint32_t e = ~row[j + 1] & S::FULLROW;
-            span[j] = (popc32(e) <= 4 && e != 0u) ? ((uint32_t)ctz32(e) | (uint32_t)(31 - clz32(e)) << 8 | 1u << 16) : 0u;
-            near |= span[j];
+            for (int j = 0; j < 3; ++j) {
+                const uint32_t e = ~row[j + 1] & S::FULLROW;
+                if (popc32(e) <= 4 && e != 0u) span[j] = (uint32_t)ctz32(e) | (uint32_t)(31 - clz32(e)) << 8 | 1u << 16;
+            }
         }
         unsigned long long m = 0ull, cs = 0ull;                // legal slots; poking slots that need the exact test
 #pragma unroll 1
@@ -855,7 +856,7 @@ TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uin
             const int sbase = l ? n0 * (C - w0 + 1) : 0;
             const uint32_t range = mask_lo(C - w + 1);
             uint32_t rescue = 0u;                              // anchor columns whose piece covers a near-full row's gap
-            if (near != 0u) {
+            if (near) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int lo = (int)(span[j] & 0xFFu), hi = (int)((span[j] >> 8) & 0xFFu);
@@ -871,6 +872,7 @@ TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uin
                 for (int dx = 0; dx < 4; ++dx)
                     if (dx < w) bad |= ((uint32_t)(gg >> (16 * (4 - ph + desc_bot(d, dx)))) & 0xFFFFu) >> dx;
                 const uint32_t ok = ~bad & range, cd = bad & rescue & range;
+                if (ANY_ONLY && ok != 0u) return 1ull;
                 // loop-local slot of (column c, orientation o) = c * n + o
                 m |= (unsigned long long)(n == 2 ? spread16(ok) << o : ok) << sbase;
                 cs |= (unsigned long long)(n == 2 ? spread16(cd) << o : cd) << sbase;

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/tetris_b200.h"
 #include "tb_core.cuh"
 
@@ -1185,13 +1187,26 @@ static int tuning_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 // dynamic shared memory above 48 KB is opt-in per kernel
+// (done once per kernel and device: the driver call costs a microsecond or two, which small-batch loops would pay per launch)
 static int opt_in_smem(const void *kernel, size_t bytes)
 {
+    static std::mutex mu;
+    static const void *seen_kernel[256];
+    static int seen_dev[256], n_seen = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (int i = 0; i < n_seen; ++i)
+            if (seen_kernel[i] == kernel && seen_dev[i] == dev) return 0;
+    }
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(shared memory %zu B): %s", bytes, cudaGetErrorString(e));
         return -2;
     }
+    std::lock_guard<std::mutex> lock(mu);
+    if (n_seen < 256) { seen_kernel[n_seen] = kernel; seen_dev[n_seen] = dev; ++n_seen; }
     return 0;
 }
 static unsigned grid_for(int64_t work_items, int per_block, int blocks_per_sm)
