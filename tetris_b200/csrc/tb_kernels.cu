@@ -337,6 +337,9 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
         __syncthreads();
         if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
         // ---- phase B (warp per window): per (piece, column loop) job; a window = EPW envs x (C - W + 1) columns
+        // windows are dealt to the warps round robin, continuing across jobs (separately for jobs of 1 and of 2
+        // orientations, which cost about 1 : 2), so the warps' totals differ by at most one window per class
+        int woff1 = 0, woff2 = 0;
         auto column_loop = [&](auto wtag, uint32_t jb, int np) {
             constexpr int W = decltype(wtag)::value;
             constexpr int NC = C - W + 1, EPW = 32 / NC;
@@ -344,7 +347,9 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             const bool lane_ok = k < EPW;
             const int p = jb & 15, l = (jb >> 4) & 1, n = (jb >> 8) & 3;
             const int nwin = (np + EPW - 1) / EPW;
-            for (int win = (warp + p + 3 * l) % NWARPS; win < nwin; win += NWARPS) {
+            const int wstart = (warp + NWARPS - (n == 2 ? woff2 : woff1) % NWARPS) % NWARPS;
+            if (n == 2) woff2 += nwin; else woff1 += nwin;
+            for (int win = wstart; win < nwin; win += NWARPS) {
                 const int idx = win * EPW + k;
                 const bool on = lane_ok && idx < np;
                 const int env = on ? (int)sm.list[p][idx] : 0;
@@ -746,6 +751,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             __syncthreads();
             if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
             // ---- phase B: score every legal placement, keep the first arg-max per env and column loop
+            int woff1 = 0, woff2 = 0;                      // round robin continued across jobs, as in K1
             auto column_loop = [&](auto wtag, uint32_t jb, int np) {
                 constexpr int W = decltype(wtag)::value;
                 constexpr int NC = C - W + 1, EPW = 32 / NC;
@@ -753,7 +759,9 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 const bool lane_ok = k < EPW;
                 const int p = jb & 15, l = (jb >> 4) & 1, n = (jb >> 8) & 3;
                 const int nwin = (np + EPW - 1) / EPW;
-                for (int win = (warp + p + 3 * l) % NWARPS; win < nwin; win += NWARPS) {
+                const int wstart = (warp + NWARPS - (n == 2 ? woff2 : woff1) % NWARPS) % NWARPS;
+                if (n == 2) woff2 += nwin; else woff1 += nwin;
+                for (int win = wstart; win < nwin; win += NWARPS) {
                     const int idx = win * EPW + k;
                     const bool on = lane_ok && idx < np;
                     const int env = on ? (int)sm.list[p][idx] : 0;
