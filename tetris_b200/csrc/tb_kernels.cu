@@ -471,8 +471,10 @@ k_afterstates_export(StateView sv, float *__restrict__ feats, uint16_t *__restri
 // ---------------------------------------------------------------------------------------------
 // K2 step
 // ---------------------------------------------------------------------------------------------
+// 8 CTAs per SM (64 registers, 16 bytes of spill): thread-per-env code is latency-bound and wants warps more than
+// registers -- 0.182 -> 0.155 ms per 2^20 envs against 5 CTAs at 96 registers; 10 / 12 CTAs (48 / 40 registers) lose again
 template <int C, int R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int32_t *__restrict__ actions,
        const uint8_t *__restrict__ tape, float *__restrict__ obs, int32_t *__restrict__ reward,
        uint8_t *__restrict__ done, int32_t *__restrict__ lines, int32_t *status, int flags, F8 dirs)
@@ -630,7 +632,7 @@ apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece
 
 // random policy: everything is per-env, one thread per env, board in registers for all n_steps
 template <int C, int R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128)                     // 94 registers; capping them at 80 / 64 changes nothing here
 k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, int64_t *stats,
                  int no_reset)
 {
