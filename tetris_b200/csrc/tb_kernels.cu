@@ -632,7 +632,7 @@ apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece
 
 // random policy: everything is per-env, one thread per env, board in registers for all n_steps
 template <int C, int R>
-__global__ void __launch_bounds__(128)                     // 94 registers; capping them at 80 / 64 changes nothing here
+__global__ void __launch_bounds__(128, 6)                  // 80 registers, no spills (measured: profiles/README.md, r1g)
 k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, int64_t *stats,
                  int no_reset)
 {
@@ -1408,7 +1408,7 @@ static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_of
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
         if (policy == TB_POLICY_RANDOM)                                                                  \
-            k_rollout_random<c, r><<<grid_for(n_env, 128, 8), 128, 0, st>>>(make_view<c, r>(state, n_env), \
+            k_rollout_random<c, r><<<grid_for(n_env, 128, 32), 128, 0, st>>>(make_view<c, r>(state, n_env), \
                 env_offset, seed, piece_set, n_steps, stats, no_reset);                                  \
         else {                                                                                           \
             typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int);          \
