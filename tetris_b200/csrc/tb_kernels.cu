@@ -1219,10 +1219,14 @@ static int opt_in_smem(const void *kernel, size_t bytes)
     if (n_seen < 256) { seen_kernel[n_seen] = kernel; seen_dev[n_seen] = dev; ++n_seen; }
     return 0;
 }
-static unsigned grid_for(int64_t work_items, int per_block, int blocks_per_sm)
+// Grid of a kernel that loops over its work items: `waves` x (SMs x resident CTAs per SM).  waves = 1 is a strictly
+// persistent grid; the tile kernels use 8 (K1) / 16 (K3) -- tiles and envs differ in cost, and handing the hardware
+// scheduler more, shorter CTAs evens the SMs out (K1 -4 %, K3 -2.7 %, random rollout -17 % against waves = 1) at the
+// price of a few more table set-ups per SM.
+static unsigned grid_for(int64_t work_items, int per_block, int blocks_per_sm, int waves = 1)
 {
     const int64_t need = (work_items + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;         // persistent: a multiple of the SM count
+    const int64_t cap = (int64_t)sm_count() * blocks_per_sm * waves;   // a multiple of the SM count
     return (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 // Tile configuration by batch size: the throughput configuration (cfg 0, 256-env tiles, thread per env) once there is
@@ -1346,7 +1350,7 @@ int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_
         else { tile = 256; minb = 3; smem = sizeof(CtaSmem<c, r, 256>);                                  \
             kern = directions ? k_afterstates<c, r, true, 256, 3> : k_afterstates<c, r, false, 256, 3>; }\
         if (opt_in_smem((const void *)kern, smem)) return -2;                                            \
-        kern<<<grid_for(n_env, tile, minb), threads ? threads : tile, smem, st>>>(make_view<c, r>(state, n_env), feats_out,  \
+        kern<<<grid_for(n_env, tile, minb, 8), threads ? threads : tile, smem, st>>>(make_view<c, r>(state, n_env), feats_out,  \
             (unsigned long long *)valid_out, count_out, a_stride, dirs, flags);                          \
         return check_launch("tb_afterstates");                                                           \
     }
@@ -1408,7 +1412,7 @@ static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_of
 #define X(c, r)                                                                                          \
     if (C == c && R == r) {                                                                              \
         if (policy == TB_POLICY_RANDOM)                                                                  \
-            k_rollout_random<c, r><<<grid_for(n_env, 128, 32), 128, 0, st>>>(make_view<c, r>(state, n_env), \
+            k_rollout_random<c, r><<<grid_for(n_env, 128, 6, 5), 128, 0, st>>>(make_view<c, r>(state, n_env), \
                 env_offset, seed, piece_set, n_steps, stats, no_reset);                                  \
         else {                                                                                           \
             typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int);          \
@@ -1425,7 +1429,7 @@ static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_of
             else { tile = 256; minb = 2; kern = k_rollout_greedy<c, r, 256, 2>;                          \
                 smem = ((sizeof(CtaSmem<c, r, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }      \
             if (opt_in_smem((const void *)kern, smem)) return -2;                                        \
-            kern<<<grid_for(n_env, tile, minb), threads ? threads : tile, smem, st>>>(                   \
+            kern<<<grid_for(n_env, tile, minb, 16), threads ? threads : tile, smem, st>>>(               \
                 make_view<c, r>(state, n_env), env_offset, seed, piece_set, n_steps, wts, stats, no_reset); \
         }                                                                                                \
         return check_launch("tb_rollout");                                                               \
