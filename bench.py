@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--rollout-steps", type=int, default=32, help="placements per env per step")
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--board", default="10x20", help="columns x rows: 10x20 (headline), 10x10, 6x12, 8x16")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="stream-pipelined chunks of the host-buffer e2e cycle")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="stream-pipelined chunks of the host-buffer e2e cycle")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu baseline / e2e side measurements")
     return ap.parse_args()
 

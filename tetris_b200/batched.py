@@ -291,7 +291,8 @@ class HostRollout:
     is keyed by its global env id (same argument as multi-GPU sharding).
     """
 
-    def __init__(self, num_columns, num_rows, n_env, chunks=4, piece_set=1, seed=0, env_offset=0, device=None):
+    def __init__(self, num_columns, num_rows, n_env, chunks=8, piece_set=1, seed=0, env_offset=0, device=None,
+                 prioritized=True):
         from .distributed import shard_range
         self.n_env, self.chunks = int(n_env), max(1, min(int(chunks), int(n_env)))
         self.bounds = []
@@ -303,7 +304,10 @@ class HostRollout:
                                            env_offset=int(env_offset) + off, device=device))
         e0 = self.envs[0]
         self.device = e0.device
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.envs]
+        # earlier chunks at higher stream priority: their rollout CTAs are scheduled first, so chunk i finishes (and its
+        # D2H copy starts) while chunk i+1 still computes, instead of all chunks' kernels sharing the SMs to the end
+        self.streams = [torch.cuda.Stream(device=self.device, priority=-(self.chunks - 1 - i) if prioritized else 0)
+                        for i in range(self.chunks)]
         self.h_rows = torch.zeros((self.n_env, e0.n_stored_rows), dtype=torch.int16).pin_memory()
         self.h_heights = torch.zeros((self.n_env, e0.num_columns), dtype=torch.uint8).pin_memory()
         self.h_piece = torch.zeros(self.n_env, dtype=torch.uint8).pin_memory()
