@@ -188,12 +188,12 @@ template <int C, int R, int TILE>
 struct CtaSmem {
     using K = Env<C, R>;
     uint32_t rec[TILE * K::WORDS];
-    uint32_t odesc[kNumOris][kOriWords]; // orientation descriptors, decoded (OriU): broadcast 128-bit loads
+    alignas(16) uint32_t odesc[kNumOris][kOriWords]; // orientation descriptors, decoded (OriU): broadcast 128-bit loads
     uint32_t vloc[TILE][2];              // K1: legal placements of each env per column loop (16 bits per orientation)
                                          // K3: best orderable score of each env per column loop
     uint32_t sloc[TILE][2];              // placements of each env that need the general evaluation (they clear a line),
                                          // per column loop, same bit layout as vloc in K1 (16 bits per orientation)
-    uint16_t run[RunTab<R>::SIZE];
+    alignas(16) uint16_t run[RunTab<R>::SIZE];
     uint8_t list[kNumPieces][TILE];      // tile-local env indices grouped by piece
     uint8_t pid[TILE];                   // piece of each env of the tile
     int cnt[2][kNumPieces + 1];          // envs per piece, double-buffered by tile / step parity
@@ -202,21 +202,67 @@ struct CtaSmem {
 };
 // K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements,
 // and per-warp episode statistics
+static_assert(sizeof(CtaSmem<10, 20, 256>) <= 76800, "K1 at 10x20 must keep fitting three 256-env CTAs per SM");
+
 template <int TILE, int THREADS = TILE> struct BestSmem {
     unsigned long long best[TILE];
     long long wstat[THREADS / 32][TB_ST_COUNT];
     uint8_t bslot[TILE][2];              // slot of the best score per column loop
 };
 
+// Compile-time images of the two shared-memory tables, copied (not computed) by every CTA: with multi-wave grids a CTA
+// often handles a single tile, and building the run table in the kernel cost about 3 % of a K1 tile.
+//   g_odesc : decode_ori() of every orientation, laid out as OriU (see kOriWords)
+//   g_run<R>: run_tab_entry<R>() of every half mask
+struct OdescImage { uint32_t w[kNumOris][kOriWords]; };
+constexpr uint32_t cx_mask(int k) { return (1u << k) - 1u; }
+constexpr OdescImage make_odesc_image()
+{
+    OdescImage t{};
+    for (int i = 0; i < kNumOris; ++i) {
+        const uint32_t d = kOriHost[i];
+        for (int dx = 0; dx < 4; ++dx) {
+            const uint32_t bot = (d >> (3 + 5 * dx)) & 3u, len = (d >> (5 + 5 * dx)) & 7u, top = bot + len;
+            t.w[i][0 + dx] = bot; t.w[i][4 + dx] = len; t.w[i][8 + dx] = top;
+            t.w[i][12 + dx] = cx_mask((int)len) << bot; t.w[i][16 + dx] = cx_mask((int)bot); t.w[i][20 + dx] = cx_mask((int)top);
+        }
+        t.w[i][24] = cx_mask((int)((d >> 23) & 7u));                 // chgm
+        t.w[i][25] = (d >> 28) & 7u;                                 // ph
+        t.w[i][26] = 2u + ((d >> 26) & 3u) + kFloatBias;             // lh2
+        t.w[i][27] = 0u;
+    }
+    return t;
+}
+__device__ const OdescImage g_odesc = make_odesc_image();
+
+template <int R> struct RunImage { alignas(16) uint16_t v[RunTab<R>::SIZE]; };
+template <int R>
+constexpr RunImage<R> make_run_image()
+{
+    RunImage<R> t{};
+    constexpr int HB = RunTab<R>::HB;
+    for (int m = 0; m < RunTab<R>::SIZE; ++m) {
+        int rs = 0;
+        for (uint32_t w = (uint32_t)m; w; w &= w >> 1)
+            for (uint32_t x = w; x; x >>= 1) rs += (int)(x & 1u);
+        int trail = 0, lead = 0;
+        while (trail < HB && ((m >> trail) & 1)) ++trail;
+        while (lead < HB && ((m >> (HB - 1 - lead)) & 1)) ++lead;
+        t.v[m] = (uint16_t)(rs | (trail << 8) | (lead << 12));
+    }
+    return t;
+}
+template <int R> __device__ const RunImage<R> g_run = make_run_image<R>();
+
 template <int C, int R, int TILE>
 __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
 {
-    if (threadIdx.x < kNumOris) {
-        sm.ori[threadIdx.x] = c_ori[threadIdx.x];
-        const OriU u = decode_ori(c_ori[threadIdx.x]);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(&u);
-        for (int i = 0; i < 27; ++i) sm.odesc[threadIdx.x][i] = w[i];
-        sm.odesc[threadIdx.x][27] = 0u;
+    if (threadIdx.x < kNumOris) sm.ori[threadIdx.x] = c_ori[threadIdx.x];
+    {
+        static_assert(sizeof(OdescImage) % 16 == 0, "odesc is copied in 128-bit words");
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_odesc.w);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.odesc);
+        for (int i = threadIdx.x; i < (int)(sizeof(OdescImage) / 16); i += blockDim.x) dst[i] = src[i];
     }
     if (threadIdx.x < kNumPieces) sm.piece[threadIdx.x] = c_piece[threadIdx.x];
     if (threadIdx.x < kNumJobs) {
@@ -229,7 +275,13 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
         sm.job[threadIdx.x] = jb;
     }
     if (threadIdx.x <= kNumPieces) { sm.cnt[0][threadIdx.x] = 0; sm.cnt[1][threadIdx.x] = 0; }
-    for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = run_tab_entry<R>((uint32_t)m);
+    if (RunTab<R>::SIZE % 8 == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_run<R>.v);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.run);
+        for (int i = threadIdx.x; i < RunTab<R>::SIZE / 8; i += blockDim.x) dst[i] = src[i];
+    } else {
+        for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = g_run<R>.v[m];
+    }
     __syncthreads();
 }
 
