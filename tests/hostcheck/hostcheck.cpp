@@ -109,3 +109,31 @@ extern "C" int hc_bag_draw(int n_set, uint64_t seed, uint64_t env, uint32_t *bag
 }
 extern "C" float hc_fitness(const float *f, const float *w) { return fitness(f, w); }
 extern "C" int hc_num_slots(int piece, int C) { return piece_num_slots(kPieceHost[piece], C); }
+
+// The compile-time table images the kernels copy must equal what decode_ori / run_tab_entry compute.
+template <int R>
+static int run_image_ok()
+{
+    static constexpr RunImage<R> img = make_run_image<R>();
+    for (int m = 0; m < RunTab<R>::SIZE; ++m)
+        if (img.v[m] != run_tab_entry<R>((uint32_t)m)) return 0;
+    return 1;
+}
+extern "C" int hc_table_images()
+{
+    static constexpr OdescImage od = make_odesc_image();
+    for (int i = 0; i < kNumOris; ++i) {
+        const OriU u = decode_ori(kOriHost[i]);
+        uint32_t w[27];
+        std::memcpy(w, &u, sizeof w);
+        for (int k = 0; k < 27; ++k)
+            if (od.w[i][k] != w[k]) return -(100 + i);
+        if (od.w[i][27] != 0u) return -(200 + i);
+    }
+    if (!run_image_ok<20>()) return -20;
+    if (!run_image_ok<10>()) return -10;
+    if (!run_image_ok<12>()) return -12;
+    if (!run_image_ok<16>()) return -16;
+    if (!run_image_ok<4>()) return -4;
+    return 0;
+}

@@ -187,3 +187,10 @@ def test_num_slots(hc):
     for Cc in (4, 6, 8, 10):
         for p in range(9):
             assert hc.hc_num_slots(p, Cc) == orc.num_afterstates(p, Cc)
+
+
+def test_compile_time_table_images(hc):
+    """The constexpr images of the run table and of the decoded orientation descriptors (copied into shared memory
+    by the tile kernels) equal run_tab_entry / decode_ori word for word, for every compiled board height."""
+    hc.hc_table_images.restype = C.c_int
+    assert hc.hc_table_images() == 0

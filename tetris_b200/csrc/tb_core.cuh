@@ -642,6 +642,51 @@ TB_HD OriU decode_ori(uint32_t d)
 }
 static_assert(sizeof(OriU) == 27 * 4, "OriU is 27 words");
 
+// ---------------------------------------------------------------------------------------------
+// Compile-time images of the two tables the tile kernels keep in shared memory:
+//   OdescImage  : decode_ori() of every orientation, laid out as OriU (kOriWords words each)
+//   RunImage<R> : run_tab_entry<R>() of every half mask
+// Plain constexpr restatements (no intrinsics), so the kernels can copy instead of compute; tests/hostcheck
+// compares them word for word with decode_ori / run_tab_entry.
+// ---------------------------------------------------------------------------------------------
+struct OdescImage { uint32_t w[kNumOris][kOriWords]; };
+constexpr uint32_t cx_mask(int k) { return (1u << k) - 1u; }
+constexpr OdescImage make_odesc_image()
+{
+    OdescImage t{};
+    for (int i = 0; i < kNumOris; ++i) {
+        const uint32_t d = kOriHost[i];
+        for (int dx = 0; dx < 4; ++dx) {
+            const uint32_t bot = (d >> (3 + 5 * dx)) & 3u, len = (d >> (5 + 5 * dx)) & 7u, top = bot + len;
+            t.w[i][0 + dx] = bot; t.w[i][4 + dx] = len; t.w[i][8 + dx] = top;
+            t.w[i][12 + dx] = cx_mask((int)len) << bot; t.w[i][16 + dx] = cx_mask((int)bot); t.w[i][20 + dx] = cx_mask((int)top);
+        }
+        t.w[i][24] = cx_mask((int)((d >> 23) & 7u));                 // chgm
+        t.w[i][25] = (d >> 28) & 7u;                                 // ph
+        t.w[i][26] = 2u + ((d >> 26) & 3u) + kFloatBias;             // lh2
+        t.w[i][27] = 0u;
+    }
+    return t;
+}
+
+template <int R> struct RunImage { alignas(16) uint16_t v[RunTab<R>::SIZE]; };
+template <int R>
+constexpr RunImage<R> make_run_image()
+{
+    RunImage<R> t{};
+    constexpr int HB = RunTab<R>::HB;
+    for (int m = 0; m < RunTab<R>::SIZE; ++m) {
+        int rs = 0;
+        for (uint32_t w = (uint32_t)m; w; w &= w >> 1)
+            for (uint32_t x = w; x; x >>= 1) rs += (int)(x & 1u);
+        int trail = 0, lead = 0;
+        while (trail < HB && ((m >> trail) & 1)) ++trail;
+        while (lead < HB && ((m >> (HB - 1 - lead)) & 1)) ++lead;
+        t.v[m] = (uint16_t)(rs | (trail << 8) | (lead << 12));
+    }
+    return t;
+}
+
 // Incremental evaluation of one placement: orientation `u` (width W) anchored at column c.  Only the piece's
 // columns and their neighbours are re-evaluated; everything else comes from the env record.  Branch-free apart
 // from the two early exits.
