@@ -25,6 +25,14 @@ if ROOT not in sys.path:
 C, R, PIECE_SET = 10, 20, 1     # --board overrides C x R (BASELINE configs[4]: 10x20, 10x10, 6x12)
 STATE_READ_BYTES = 64          # 3 x 128-bit row planes + 128-bit meta per env (include/tetris_b200.h)
 METRIC = "placements/sec (env steps/sec), greedy-linear policy, whole job"
+# The reference itself is pure Python and does not travel to the GPU box (no /root/reference there), so its own speed
+# rides along as a labelled constant: measured in the build container (SURVEY.md section 6 / BASELINE.md section 2).
+PYTHON_REFERENCE = {
+    "value": 200.0, "unit": "placements/s", "cores": 1, "kind": "reference (Python, unmodified), constant -- not timed in this run",
+    "provenance": "SURVEY.md section 6: corrected example_play.py loop, 10x20, 7-piece set, greedy BCTS argmax, 300 "
+                  "placements, 1 core of the build container's 8-vCPU Xeon, NumPy 2.3.5 / CPython 3.12.3 "
+                  "(random policy: 170 placements/s; afterstate feature vectors: 3.2-4.7 k/s)",
+}
 
 
 def parse():
@@ -183,12 +191,19 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = n_env * T * args.steps / dt
     sample = "%d envs x %d placements per step on %d host threads (C port of the reference loop)" % (n_env, T, threads)
+    cfg = config_of(args, args.gpus)
+    # same workload (board, pieces, policy, placements per step); the env count is this arm's own bounded sample -- a
+    # CPU's rate does not depend on it -- and is stated as such instead of the GPU arm's 2^20 per GPU
+    cfg.update({"envs_per_gpu": None, "total_envs": n_env, "envs_cpu_sample": n_env,
+                "workload": cfg["workload"].replace("%d envs/GPU" % args.envs, "%d envs (bounded CPU sample)" % n_env),
+                "l2": "n/a (CPU)", "parallelism": "%d host threads, envs split evenly" % threads})
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-        "data": "synthetic", "config": config_of(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "placements/s", "cores": threads, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "placements/s", "cores": threads, "kind": "port", "sample": sample,
+                         "python_reference": PYTHON_REFERENCE},
         "e2e": {"value": value, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -211,8 +226,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("TB_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")              # stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG", "WARN")                          # a caller's (the driver's) setting is kept
         dist.init_process_group("nccl", device_id=dev)
     K, W, T, E = args.steps, args.warmup, args.rollout_steps, args.envs
     W = max(W, 3)
@@ -223,11 +237,13 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     weights = np.asarray(BCTS_WEIGHTS, np.float32)
 
+    reduced = torch.zeros_like(env.stats)
+
     def step():
         env.rollout(T, "greedy", weights)
         if world > 1:
-            return reduce_stats(env.stats)                   # end-of-rollout reduction of episode statistics (NCCL)
-        return env.stats
+            return reduce_stats(env.stats, out=reduced)      # end-of-rollout reduction of episode statistics: ONE
+        return env.stats                                     # NCCL all-gather + a one-warp combine kernel
 
     sampler = ClockSampler(local)
     sampler.start()                                          # nvidia-smi takes a moment to start: begin before warm-up
@@ -258,12 +274,26 @@ def run_ours(args):
     ms = float(t_ms.item())
     placements = float(world) * E * T * K
     value = placements / (ms * 1e-3)
+    # The reduced episode statistics of the whole job (all ranks, warm-up + timed steps; the statistics were zeroed
+    # after the untimed random warm-up), with the integer invariants every correct run satisfies -- evidence that all
+    # ranks took part in the reduction and that every env made every placement.
+    final = (reduced if world > 1 else env.stats).cpu().tolist()
+    red = dict(zip(_lib.STATS, final))
+    want = world * E * T * (W + K)
+    if red["placements"] != want or sum(red["lines%d" % i] for i in range(5)) != red["placements"] \
+            or red["lines"] != sum(i * red["lines%d" % i] for i in range(5)) \
+            or red["reward"] != red["lines"] - red["placements"] - 100 * red["episodes"]:
+        raise SystemExit("bench.py: reduced episode statistics violate their invariants: %r (expected %d placements)"
+                         % (red, want))
 
     out = {
         "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic", "config": config_of(args, world),
-        "clocks": clocks, "gpu_launches": K, "wall_s_timed_region": wall,
+        "clocks": clocks, "gpu_launches": K * (2 if world > 1 else 1), "wall_s_timed_region": wall,
+        "episode_stats_reduced": {k: red[k] for k in _lib.STATS if not k.startswith("reserved")},
+        "episode_stats_invariants": "ok: placements == world x envs x rollout_steps x (warmup + steps) = %d; "
+                                    "lines0..4 sum to placements; lines and reward follow from the histogram" % want,
         "dtype_note": "u32 column bit masks; features / scores leave the kernels as float32 (exact small integers, half-integers)",
     }
 
@@ -459,7 +489,7 @@ def run_ours(args):
             threads = os.cpu_count() or 1
             v, av, sample = cpu_port_rate(12.0, threads)
             out["cpu_baseline"] = {"value": v, "unit": "placements/s", "cores": threads, "kind": "port",
-                                   "sample": sample, "afterstates_per_s": av}
+                                   "sample": sample, "afterstates_per_s": av, "python_reference": PYTHON_REFERENCE}
 
     if rank == 0:
         print(json.dumps(out))

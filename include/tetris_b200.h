@@ -15,8 +15,11 @@
  *     allocated inside; launches are asynchronous on the caller's cudaStream_t (`stream`).
  *   - no global mutable state besides per-device __constant__ tables: safe from several host
  *     threads on distinct streams / devices.
- *   - board shape (num_columns C, num_rows R) selects a compiled template instantiation;
- *     tb_supported_shape() says which exist (10x20, 10x10, 6x12, 8x16, 4x4 ... see tb_kernels.cu).
+ *   - board shape (num_columns C, num_rows R) selects a compiled template instantiation (one translation unit per
+ *     shape, csrc/tb_shape.cu); tb_supported_shape() says which are loaded (built in: 10x20, 10x10, 6x12, 8x16, 4x4,
+ *     16x28, 12x24).  The reference takes any num_columns / num_rows (game.py:21-31): any other shape with
+ *     4 <= C <= 16 and 4 <= R <= 28 (uint16 row masks, 32-bit column masks) is compiled into its own shared object
+ *     and added with tb_load_shape().
  *
  * Device state ("state" below) is one caller-owned allocation of tb_state_bytes() bytes, 256-byte
  * aligned, laid out as a structure of arrays over envs:
@@ -43,7 +46,7 @@
 extern "C" {
 #endif
 
-#define TB_VERSION 100          /* 0.1.0 */
+#define TB_VERSION 200          /* 0.2.0 */
 #define TB_NUM_FEATURES 8
 #define TB_MAX_SLOTS 36         /* ThreeL at C = 10 */
 
@@ -52,6 +55,8 @@ extern "C" {
 #define TB_FLAG_ACTION_IS_SLOT 2   /* step: actions index enumeration slots instead of non-terminal ranks   */
 #define TB_FLAG_INCLUDE_TERMINAL 4 /* afterstates: also write the feature rows of terminal afterstates
                                       (get_after_states(include_terminal=True), game.py:74-78)               */
+#define TB_FLAG_VALIDATE_ONLY  8   /* step: dry run -- only status_out is produced, no env is touched; lets a caller
+                                      raise the reference's IndexError (game.py:83) BEFORE any env is stepped  */
 
 /* tb_rollout policies */
 #define TB_POLICY_RANDOM 0         /* uniformly random legal placement (per-env counter RNG, stream 1)       */
@@ -69,8 +74,22 @@ enum {
 int tb_version(void);
 const char *tb_last_error(void);
 
-/* 1 if kernels for this board shape were compiled in. */
+/* 1 if kernels for this board shape are loaded (built in, or added with tb_load_shape). */
 int tb_supported_shape(int num_columns, int num_rows);
+/*
+ * Add the kernels of one more board shape: `path` is a shared object built from csrc/tb_shape.cu with
+ * -DTB_C=<num_columns> -DTB_R=<num_rows> -DTB_SHAPE_PLUGIN (tetris_b200._lib.build_shape does it).  The object stays
+ * loaded for the life of the process.  Tetris(num_columns, num_rows) of the reference takes any size (game.py:21-31).
+ */
+int tb_load_shape(const char *path);
+/*
+ * Tuning knobs for experiments and tests; the defaults are what ships.  Names: "k1_cfg" / "k3_cfg" (tile configuration
+ * of tb_afterstates / tb_rollout, -1 = chosen by batch size), "small_groups", "max_ctas" (0 = no cap; a small cap makes
+ * every CTA loop over several tiles).  Defaults may also come from the environment (TB_K1_CFG, TB_K3_CFG,
+ * TB_SMALL_GROUPS, TB_MAX_CTAS), which is read once.  tb_get_tuning returns the current value.
+ */
+int tb_set_tuning(const char *name, int value);
+int tb_get_tuning(const char *name);
 /* Bytes of device state for n_env envs (0 if the shape is unsupported). */
 size_t tb_state_bytes(int num_columns, int num_rows, int64_t n_env);
 /* Number of afterstates (enumeration slots) of a piece: SURVEY.md Appendix A. */
@@ -88,7 +107,8 @@ int tb_a_max(int num_columns, int piece_set);
  * Tetris.__init__ + reset (game.py:21-63): empty boards, fresh bags, zero counters, draw the first piece.
  *   env_offset  global id of env 0 of this shard (per-env RNG is keyed by seed and GLOBAL env id, so results do
  *               not depend on how envs are sharded over GPUs)
- *   piece_tape  nullable uint8[n_env]: global piece ids to use instead of the bag RNG (parity runs)
+ *   piece_tape  nullable uint8[n_env]: global piece ids to use instead of the bag RNG (parity runs); an id that
+ *               names no piece leaves the env inert (no afterstates, never stepped)
  *   reset_mask  nullable uint8[n_env]: if given, behaves like Tetris.reset() (game.py:53-63) on the flagged
  *               envs only -- board emptied, one more piece drawn, the bag persists
  */
@@ -99,15 +119,17 @@ int tb_reset(void *state, int num_columns, int num_rows, int64_t n_env, int64_t 
  * Tetris.get_after_states (game.py:67-80) for every env: enumerate every rotation x column placement of the
  * current piece (tetromino.py:*.get_after_states), drop, lock, clear (state.py:121-143), terminal test
  * (state.py:111-117) and the eight BCTS features (state.py:97-107,175-280).
- *   feats_out   float32[n_env][a_stride][8], by enumeration slot.  Rows of non-terminal afterstates (the ones
- *               game.py:69 keeps) are always written; rows of terminal afterstates only with
+ *   feats_out   float32[n_env][a_stride][8], by enumeration slot, 16-byte aligned.  Rows of non-terminal afterstates
+ *               (the ones game.py:69 keeps) are always written; rows of terminal afterstates only with
  *               TB_FLAG_INCLUDE_TERMINAL (game.py:74-78); rows >= tb_num_slots(piece) never.
+ *   a_stride    row stride of feats_out in afterstates, 1..64; normally tb_a_max().  Slots >= a_stride are not
+ *               written (their legality is still reported in valid_out / count_out).
  *   valid_out   nullable uint64[n_env]: bit s set  <=>  slot s is a non-terminal afterstate (a legal action)
  *   count_out   nullable int32[n_env]: number of legal actions (len(self.afterstates), game.py:69)
  *   directions  nullable HOST float[8]: per-feature multipliers (feature_directions, state.py:49-50), applied in fp32
  *   flags       0 or TB_FLAG_INCLUDE_TERMINAL
  */
-int tb_afterstates(const void *state, int num_columns, int num_rows, int64_t n_env, float *feats_out,
+int tb_afterstates(const void *state, int num_columns, int num_rows, int64_t n_env, void *feats_out,
                    uint64_t *valid_out, int32_t *count_out, int a_stride, const float *directions, int flags,
                    void *stream);
 
@@ -129,8 +151,11 @@ int tb_afterstates_export(const void *state, int num_columns, int num_rows, int6
  *   obs_out     nullable float32[n_env][8]: features of the chosen afterstate (game.py:91)
  *   reward_out  nullable int32[n_env]: lines - 1, and -100 more when done (game.py:86-90)
  *   done_out    nullable uint8[n_env]; lines_out nullable int32[n_env]
- *   status_out  nullable int32[1]: set non-zero if any action was out of range (the reference raises IndexError,
- *               game.py:83); such envs are left untouched
+ *   status_out  nullable int32[1], zeroed by the caller: left 0 if every action was in range, else
+ *               0x7FFFFFFF - (lowest env index with an out-of-range action).  The reference raises IndexError
+ *               (game.py:83); here such an env is left untouched and its outputs are defined: zero observation,
+ *               reward and lines, done = the env has no legal placement at all.  With TB_FLAG_VALIDATE_ONLY nothing
+ *               but status_out is written and no env is stepped.
  */
 int tb_step(void *state, int num_columns, int num_rows, int64_t n_env, int64_t env_offset, uint64_t seed,
             int piece_set, const int32_t *actions, const uint8_t *piece_tape, float *obs_out, int32_t *reward_out,
@@ -153,18 +178,24 @@ int tb_rollout(void *state, int num_columns, int num_rows, int64_t n_env, int64_
  *   child_state caller-owned scratch of tb_state_bytes(C, R, n_env * a_stride * n_forks) bytes; child
  *               d = (e * a_stride + s) * n_forks + f draws pieces from the stream (seed2, child_offset + d), starting
  *               from the parent's bag (the reference forks share one global sampler and are not reproducible)
+ *   piece_tape  nullable uint8[n_env * a_stride * n_forks][length]: the pieces child d draws, in order (the one drawn
+ *               by the action itself first), instead of its RNG stream -- what a recorded sampler of the reference
+ *               supplies (parity runs against game.py:129-160)
  *   ret_sum     int32[n_env][a_stride]: sum of the forks' returns (mean = ret_sum / n_forks); 0 for illegal slots
  *   valid_out   nullable uint64[n_env]: legal slots
  *   stats       int64[TB_ST_COUNT] device: statistics of the follow-up placements are added (as tb_rollout)
  */
 int tb_rollout_values(const void *state, int num_columns, int num_rows, int64_t n_env, int piece_set, void *child_state,
                       int a_stride, int n_forks, int length, int policy, const float *weights, uint64_t seed2,
-                      int64_t child_offset, int32_t *ret_sum, uint64_t *valid_out, int64_t *stats, void *stream);
+                      int64_t child_offset, const uint8_t *piece_tape, int32_t *ret_sum, uint64_t *valid_out,
+                      int64_t *stats, void *stream);
 
 /*
  * State interchange (state.py:22-25,162-172; utils.py:179-191 needs the board on the host).
  * export: rows_out uint16[count][R+4], heights_out uint8[count][C], piece_out uint8[count] (all nullable)
- * import: rows_in  uint16[count][R+4] (heights are recomputed), piece_in nullable uint8[count]
+ * import: rows_in  uint16[count][R+4] (heights are recomputed), piece_in nullable uint8[count].  A board with a cell at
+ *         or above row R is a terminal state (state.py:111-117): its env is marked finished (piece 0xFF) -- it has no
+ *         afterstates and no kernel steps it.  A piece id that names no piece makes the env inert (0xFE).
  */
 int tb_export_boards(const void *state, int num_columns, int num_rows, int64_t n_env, int64_t first, int64_t count,
                      uint16_t *rows_out, uint8_t *heights_out, uint8_t *piece_out, void *stream);
@@ -201,6 +232,13 @@ int tb_fitness(int64_t n, const float *feats, const float *weights, float *out, 
 int tb_action_probabilities(int64_t n_env, int a_stride, const float *feats, const uint64_t *valid,
                             const double *weights, double temperature, const int32_t *actions, double *probs_out,
                             double *grad_out, void *stream);
+
+/*
+ * Combine n_parts episode-statistics vectors (int64[n_parts][TB_ST_COUNT], device) into out int64[TB_ST_COUNT]:
+ * sums, except the two maxima.  The local half of the multi-GPU reduction: one all-gather of the ranks' vectors,
+ * then this (tetris_b200.distributed.reduce_stats).
+ */
+int tb_combine_stats(const int64_t *parts, int n_parts, int64_t *out, void *stream);
 
 #ifdef __cplusplus
 }

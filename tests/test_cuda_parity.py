@@ -487,15 +487,26 @@ def test_host_rollout_equals_resident(chunks):
 
 
 @pytest.mark.parametrize("k1cfg,k3cfg", [(0, 0), (2, 0), (3, 2), (3, 3), (4, 4), (5, 5)])
-def test_tile_configurations(k1cfg, k3cfg, monkeypatch):
+def test_tile_configurations(k1cfg, k3cfg):
     """tb_afterstates / tb_rollout pick a CTA tile configuration by batch size (throughput: 256-env tiles; small
     batches: 128-env tiles, or 32 / 64 envs with several warps per env group).  Every configuration must give the
     oracle's results: forced here through the library's tuning variables on a batch with ragged tiles, on a board where
     line clears and game overs are frequent and on the headline board."""
     from oracle import oracle as orc
     from tetris_b200 import BatchedTetris
-    monkeypatch.setenv("TB_K1_CFG", str(k1cfg))
-    monkeypatch.setenv("TB_K3_CFG", str(k3cfg))
+    from tetris_b200 import _lib
+    _lib.set_tuning("k1_cfg", k1cfg)
+    _lib.set_tuning("k3_cfg", k3cfg)
+    try:
+        _tile_configuration_body()
+    finally:
+        _lib.set_tuning("k1_cfg", -1)
+        _lib.set_tuning("k3_cfg", -1)
+
+
+def _tile_configuration_body():
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
     for (Cc, R, n, T) in ((6, 12, 1337, 40), (10, 20, 777, 60)):
         env = BatchedTetris(Cc, R, n, piece_set=1, seed=77)
         ob = orc.Batch(Cc, R, n, piece_set=1, seed=77)

@@ -9,15 +9,21 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("TB_SO_PATH") or os.path.join(CSRC, "libtetris_b200.so")   # override: experiments only
-SOURCES = [os.path.join(CSRC, "tb_kernels.cu"), os.path.join(CSRC, "tb_core.cuh"),
-           os.path.join(os.path.dirname(_HERE), "include", "tetris_b200.h")]
+_INC = os.path.join(os.path.dirname(_HERE), "include", "tetris_b200.h")
+SHAPE_DEPS = [os.path.join(CSRC, f) for f in ("tb_shape.cu", "tb_kernels.cuh", "tb_core.cuh", "tb_shape.h")] + [_INC]
+ABI_DEPS = [os.path.join(CSRC, f) for f in ("tb_abi.cu", "tb_core.cuh", "tb_shape.h")] + [_INC]
+SOURCES = sorted(set(SHAPE_DEPS + ABI_DEPS))
+# board shapes linked into libtetris_b200.so (columns, rows); any other 4..16 x 4..28 shape: build_shape() + tb_load_shape
+BUILTIN_SHAPES = ((10, 20), (10, 10), (6, 12), (8, 16), (4, 4))
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(CSRC, "build")
 
 NUM_FEATURES = 8
 FLAG_AUTO_RESET = 1
 FLAG_ACTION_IS_SLOT = 2
 FLAG_INCLUDE_TERMINAL = 4
+FLAG_VALIDATE_ONLY = 8
 POLICY_RANDOM = 0
 POLICY_GREEDY = 1
 STATS = ("placements", "episodes", "lines", "reward", "afterstates",
@@ -26,21 +32,98 @@ STATS = ("placements", "episodes", "lines", "reward", "afterstates",
 STATS_MAX_FIELDS = (10, 11)
 
 
-def _stale():
-    if not os.path.exists(SO_PATH):
+def _newer(deps, target):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(SO_PATH)
-    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in SOURCES)
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+def _stale():
+    return _newer(SOURCES, SO_PATH)
+
+
+def _nvcc():
+    return os.environ.get("NVCC") or "nvcc"
+
+
+def _shape_obj(c, r):
+    return os.path.join(BUILD_DIR, "tb_shape_%dx%d.o" % (c, r))
+
+
+def build(force=False, verbose=False, shapes=None):
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU): one object per board
+    shape (tb_shape.cu -DTB_C -DTB_R), compiled in parallel, plus the ABI object, linked into libtetris_b200.so."""
+    shapes = tuple(shapes or BUILTIN_SHAPES)
     if not (force or _stale()):
         return SO_PATH
-    nvcc = os.environ.get("NVCC") or "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0]]
-    subprocess.check_call(cmd, cwd=CSRC)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    jobs = []
+    for (c, r) in shapes:
+        obj = _shape_obj(c, r)
+        if force or _newer(SHAPE_DEPS, obj):
+            jobs.append((obj, [_nvcc()] + NVCC_FLAGS + extra + ["-DTB_C=%d" % c, "-DTB_R=%d" % r, "-c", "-o", obj,
+                                                                os.path.join(CSRC, "tb_shape.cu")]))
+    abi_obj = os.path.join(BUILD_DIR, "tb_abi.o")
+    # the list of linked-in shapes is a generated header of the ABI object: rewritten only when the list changes
+    inc = os.path.join(BUILD_DIR, "tb_builtin_shapes.inc")
+    text = "#define TB_BUILTIN_SHAPES(X) " + " ".join("X(%d, %d)" % s for s in shapes) + "\n"
+    if not os.path.exists(inc) or open(inc).read() != text:
+        open(inc, "w").write(text)
+    if force or _newer(ABI_DEPS + [inc], abi_obj):
+        jobs.append((abi_obj, [_nvcc()] + NVCC_FLAGS + extra + ["-c", "-o", abi_obj, os.path.join(CSRC, "tb_abi.cu")]))
+    procs = []
+    max_par = max(1, min(len(jobs), os.cpu_count() or 1))
+    pending = list(jobs)
+    failed = None
+    while pending or procs:
+        while pending and len(procs) < max_par:
+            obj, cmd = pending.pop(0)
+            procs.append((obj, cmd, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        obj, cmd, p = procs.pop(0)
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            failed = failed or (cmd, out)
+    if failed:
+        raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(failed[0]), failed[1]))
+    objs = [_shape_obj(c, r) for (c, r) in shapes] + [abi_obj]
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs + ["-ldl"],
+                          cwd=CSRC)
     return SO_PATH
+
+
+def shape_plugin_path(c, r):
+    return os.path.join(CSRC, "libtb_shape_%dx%d.so" % (c, r))
+
+
+def build_shape(c, r, force=False):
+    """Compile the kernels of one more board shape into their own in-tree shared object (needs nvcc; ~1 minute)."""
+    c, r = int(c), int(r)
+    if not (4 <= c <= 16 and 4 <= r <= 28):
+        raise ValueError("board shape %dx%d is outside 4..16 columns x 4..28 rows (uint16 row masks, 32-bit column masks)" % (c, r))
+    path = shape_plugin_path(c, r)
+    if force or _newer(SHAPE_DEPS, path):
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-shared", "-DTB_SHAPE_PLUGIN", "-DTB_C=%d" % c, "-DTB_R=%d" % r,
+                                                       "-o", path, os.path.join(CSRC, "tb_shape.cu")], cwd=CSRC)
+    return path
+
+
+def ensure_shape(c, r):
+    """Make board shape c x r available: built in, already loaded, an in-tree shape object, or compiled now (the
+    reference's Tetris takes any num_columns / num_rows, game.py:21-31).  Raises when it cannot be provided."""
+    L = lib()
+    if L.tb_supported_shape(int(c), int(r)):
+        return
+    path = shape_plugin_path(int(c), int(r))
+    if _newer(SHAPE_DEPS, path):
+        import shutil
+        if shutil.which(_nvcc()) is None:
+            raise ValueError("board shape %dx%d is not compiled in and nvcc is not available to build it" % (c, r))
+        build_shape(c, r)
+    check(L.tb_load_shape(path.encode()))
 
 
 _lib = None
@@ -84,7 +167,15 @@ def lib():
     L.tb_eval_states.restype = i32
     L.tb_eval_states.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
     L.tb_rollout_values.restype = i32
-    L.tb_rollout_values.argtypes = [vp, i32, i32, i64, i32, vp, i32, i32, i32, i32, vp, u64, i64, vp, vp, vp, vp]
+    L.tb_rollout_values.argtypes = [vp, i32, i32, i64, i32, vp, i32, i32, i32, i32, vp, u64, i64, vp, vp, vp, vp, vp]
+    L.tb_load_shape.restype = i32
+    L.tb_load_shape.argtypes = [C.c_char_p]
+    L.tb_set_tuning.restype = i32
+    L.tb_set_tuning.argtypes = [C.c_char_p, i32]
+    L.tb_get_tuning.restype = i32
+    L.tb_get_tuning.argtypes = [C.c_char_p]
+    L.tb_combine_stats.restype = i32
+    L.tb_combine_stats.argtypes = [vp, i32, vp, vp]
     L.tb_action_probabilities.restype = i32
     L.tb_action_probabilities.argtypes = [i64, i32, vp, vp, vp, C.c_double, vp, vp, vp, vp]
     L.tb_slot_info.restype = i32
@@ -97,9 +188,19 @@ def lib():
 
 EXPORTS = ("tb_version", "tb_last_error", "tb_supported_shape", "tb_state_bytes", "tb_num_slots", "tb_a_max",
            "tb_reset", "tb_afterstates", "tb_afterstates_export", "tb_step", "tb_rollout", "tb_export_boards",
-           "tb_import_boards", "tb_eval_states", "tb_slot_info", "tb_fitness", "tb_rollout_values", "tb_action_probabilities")
+           "tb_import_boards", "tb_eval_states", "tb_slot_info", "tb_fitness", "tb_rollout_values", "tb_action_probabilities",
+           "tb_load_shape", "tb_set_tuning", "tb_get_tuning", "tb_combine_stats")
 
 
 def check(rc):
     if rc != 0:
         raise RuntimeError("tetris_b200: %s" % lib().tb_last_error().decode())
+
+
+def set_tuning(name, value):
+    """Experiments / tests: force a tile configuration or cap the grid (see tb_set_tuning in include/tetris_b200.h)."""
+    check(lib().tb_set_tuning(name.encode(), int(value)))
+
+
+def get_tuning(name):
+    return lib().tb_get_tuning(name.encode())

@@ -40,8 +40,7 @@ class _Ctx:
     def __init__(self, Cc, R):
         L = _lib.lib()
         torch = _torch()
-        if not L.tb_supported_shape(Cc, R):
-            raise ValueError("board shape %dx%d is not compiled in (see TB_SHAPES in csrc/tb_kernels.cu)" % (Cc, R))
+        _lib.ensure_shape(Cc, R)                   # built in, or compiled on demand (any size: game.py:21-31)
         self.C, self.R, self.N = Cc, R, R + 4
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev

@@ -17,6 +17,11 @@ from . import BCTS_WEIGHTS, _lib
 _PIECE_SET_NAMES = {"default": 0, "threes": 0, 0: 0, "tetrominoes": 1, "seven": 1, 1: 1}
 
 
+def _lib_piece_names():
+    from . import PIECE_NAMES
+    return PIECE_NAMES
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -30,9 +35,7 @@ class BatchedTetris:
         self.num_columns, self.num_rows = int(num_columns), int(num_rows)
         self.n_env, self.seed, self.env_offset = int(n_env), int(seed) & (2 ** 64 - 1), int(env_offset)
         self.piece_set = _PIECE_SET_NAMES[piece_set]
-        if not L.tb_supported_shape(self.num_columns, self.num_rows):
-            raise ValueError("board shape %dx%d is not compiled in (see TB_SHAPES in csrc/tb_kernels.cu)"
-                             % (self.num_columns, self.num_rows))
+        _lib.ensure_shape(self.num_columns, self.num_rows)   # built in, or compiled on demand (game.py:21-31: any size)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.a_max = L.tb_a_max(self.num_columns, self.piece_set)
@@ -65,6 +68,15 @@ class BatchedTetris:
             return x.to(device=self.device, dtype=torch.uint8).contiguous()
         return torch.as_tensor(np.ascontiguousarray(x, dtype=np.uint8), device=self.device)
 
+    def _dev_pieces(self, x):
+        """Piece ids for the device.  Host arrays are checked here (ids 0..8); ids in device tensors are checked by
+        the kernels, where an id that names no piece makes the env inert."""
+        if x is not None and not isinstance(x, torch.Tensor):
+            a = np.asarray(x)
+            if a.size and (a.min() < 0 or a.max() >= len(_lib_piece_names())):
+                raise ValueError("piece ids must be in 0..%d" % (len(_lib_piece_names()) - 1))
+        return self._dev_u8(x)
+
     def set_directions(self, feature_directions):
         """feature_directions (state.py:49-50): per-feature multipliers applied to get_after_states / step obs."""
         if feature_directions is None:
@@ -77,14 +89,14 @@ class BatchedTetris:
     # -- reference surface, batched ---------------------------------------------------------
     def reset(self, tape=None):
         """Tetris.__init__ + reset for every env (game.py:21-63).  tape: uint8[n_env] first pieces (global ids)."""
-        t = self._dev_u8(tape)
+        t = self._dev_pieces(tape)
         with self._on_device():
             _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
                                            _ptr(t), None, self._stream()))
 
     def reset_masked(self, mask, tape=None):
         """Tetris.reset() (game.py:53-63) on the envs where mask is set: board emptied, one more piece drawn."""
-        m, t = self._dev_u8(mask), self._dev_u8(tape)
+        m, t = self._dev_u8(mask), self._dev_pieces(tape)
         with self._on_device():
             _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
                                            _ptr(t), _ptr(m), self._stream()))
@@ -112,27 +124,36 @@ class BatchedTetris:
         return feats, valid, count
 
     def step(self, actions, tape=None, auto_reset=False, action_is_slot=False, check=True):
-        """Tetris.step for every env (game.py:82-92).  Returns (obs f32[n,8], reward i32[n], done bool[n], lines i32[n])."""
+        """Tetris.step for every env (game.py:82-92).  Returns (obs f32[n,8], reward i32[n], done bool[n], lines i32[n]).
+
+        check=True: like the reference, an out-of-range action raises IndexError BEFORE any env is stepped (a dry run
+        of the kernel validates all actions first; one extra launch and a host synchronisation).  check=False is the
+        asynchronous path (CUDA graphs, benchmarks): an env with an out-of-range action is left untouched and reports
+        a zero observation / reward / lines and done = "no legal placement at all"."""
         if isinstance(actions, torch.Tensor):
             a = actions.to(device=self.device, dtype=torch.int32).contiguous()
         else:
             a = torch.as_tensor(np.ascontiguousarray(actions, dtype=np.int32), device=self.device)
         if a.shape != (self.n_env,):
             raise ValueError("actions must have shape (n_env,)")
-        t = self._dev_u8(tape)
+        t = self._dev_pieces(tape)
         obs = torch.empty((self.n_env, 8), dtype=torch.float32, device=self.device)
         reward = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
         done = torch.empty(self.n_env, dtype=torch.uint8, device=self.device)
         lines = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
         flags = (_lib.FLAG_AUTO_RESET if auto_reset else 0) | (_lib.FLAG_ACTION_IS_SLOT if action_is_slot else 0)
+        L = _lib.lib()
         with self._on_device():
             if check:
                 self._status.zero_()
-            _lib.check(_lib.lib().tb_step(*self._common(), self.env_offset, self.seed, self.piece_set, _ptr(a), _ptr(t),
-                                          _ptr(obs), _ptr(reward), _ptr(done), _ptr(lines),
-                                          _ptr(self._status) if check else None, flags, self._stream()))
-            if check and int(self._status.item()) != 0:
-                raise IndexError("action out of range for at least one env (game.py:83)")
+                _lib.check(L.tb_step(*self._common(), self.env_offset, self.seed, self.piece_set, _ptr(a), _ptr(t),
+                                     None, None, None, None, _ptr(self._status), flags | _lib.FLAG_VALIDATE_ONLY,
+                                     self._stream()))
+                st = int(self._status.item())
+                if st != 0:
+                    raise IndexError("action out of range for env %d (game.py:83); no env was stepped" % (0x7FFFFFFF - st))
+            _lib.check(L.tb_step(*self._common(), self.env_offset, self.seed, self.piece_set, _ptr(a), _ptr(t),
+                                 _ptr(obs), _ptr(reward), _ptr(done), _ptr(lines), None, flags, self._stream()))
         if self._dirs is not None:
             obs = obs * torch.as_tensor(self._dirs, device=self.device)
         return obs, reward, done.bool(), lines
@@ -147,7 +168,7 @@ class BatchedTetris:
                                              pol, w.ctypes.data_as(C.c_void_p), _ptr(self.stats), self._stream()))
         return self.stats
 
-    def rollout_values(self, length=5, n=5, policy="greedy", weights=None, seed=None):
+    def rollout_values(self, length=5, n=5, policy="greedy", weights=None, seed=None, piece_tape=None):
         """Tetris.perform_rollouts (game.py:150-160) for every env and every legal action at once, on the device.
 
         Every (env, action) is forked n times: the action is applied, the next piece drawn from the fork's own
@@ -155,12 +176,17 @@ class BatchedTetris:
         [n_env, a_max] -- -1 for a fork that ended, else lines minus placements of the follow-up steps, 0 where the
         slot is not a legal action --, valid int64[n_env] bit mask of legal slots).  The envs themselves are not
         stepped.  Follow-up statistics are added to self.stats.
+        piece_tape: optional uint8[n_env, a_max, n, length] -- the pieces each fork draws (the one after the action
+        first) instead of its RNG stream: what a recorded sampler of the reference supplies.
         """
         pol = {"random": _lib.POLICY_RANDOM, "greedy": _lib.POLICY_GREEDY, 0: 0, 1: 1}[policy]
         w = np.ascontiguousarray(BCTS_WEIGHTS if weights is None else weights, dtype=np.float32)
         seed2 = (self.seed ^ 0xF02C) if seed is None else int(seed) & (2 ** 64 - 1)
         L = _lib.lib()
         n_child = self.n_env * self.a_max * int(n)
+        tape = self._dev_pieces(piece_tape)
+        if tape is not None and tape.numel() != n_child * int(length):
+            raise ValueError("piece_tape must have shape (n_env, a_max, n, length)")
         with self._on_device():
             child = torch.empty(L.tb_state_bytes(self.num_columns, self.num_rows, n_child), dtype=torch.uint8,
                                 device=self.device)
@@ -168,7 +194,7 @@ class BatchedTetris:
             valid = torch.empty(self.n_env, dtype=torch.int64, device=self.device)
             _lib.check(L.tb_rollout_values(*self._common(), self.piece_set, _ptr(child), self.a_max, int(n), int(length),
                                            pol, w.ctypes.data_as(C.c_void_p), seed2,
-                                           self.env_offset * self.a_max * int(n), _ptr(ret), _ptr(valid),
+                                           self.env_offset * self.a_max * int(n), _ptr(tape), _ptr(ret), _ptr(valid),
                                            _ptr(self.stats), self._stream()))
         return ret.double() / float(n), valid
 
@@ -257,7 +283,7 @@ class BatchedTetris:
             r = torch.as_tensor(r.view(np.int16), device=self.device)
         if r.dim() != 2 or r.shape[1] != self.n_stored_rows:
             raise ValueError("rows must have shape (count, num_rows + 4)")
-        p = self._dev_u8(piece)
+        p = self._dev_u8(piece) if isinstance(piece, torch.Tensor) else self._dev_pieces(piece)
         with self._on_device():
             _lib.check(_lib.lib().tb_import_boards(*self._common(), first, r.shape[0], _ptr(r), _ptr(p), self._stream()))
 
@@ -277,6 +303,20 @@ class BatchedTetris:
         """(num_rows+4, num_columns) int64 0/1 array of one env, the reference's State.representation."""
         rows = self.export_boards(env, 1)[0].cpu().numpy().view(np.uint16)[0]
         return ((rows[:, None] >> np.arange(self.num_columns, dtype=np.uint16)) & 1).astype(np.int64)
+
+    def board_string(self, env=0):
+        """utils.print_board_to_string (utils.py:179-191) of one env of the batch: the board with its 4 buffer rows."""
+        from .utils import print_board_to_string
+        from types import SimpleNamespace
+        return print_board_to_string(SimpleNamespace(representation=self.representation(env),
+                                                     num_rows=self.n_stored_rows, num_columns=self.num_columns))
+
+    def render(self, env=0):
+        """Tetris.render (game.py:122-124) for one env of the batch: prints the board and the current piece."""
+        from . import PIECE_NAMES
+        print(self.board_string(env))
+        p = int(self.export_boards(env, 1)[2].item())
+        print(PIECE_NAMES[p] if p < len(PIECE_NAMES) else "(finished)")
 
 
 class HostRollout:

@@ -75,6 +75,11 @@ TB_HD int run_sum(uint32_t w)
 // ---------------------------------------------------------------------------------------------
 constexpr int kNumPieces = 9;
 constexpr int kNumOris = 25;
+// piece byte of an env that takes no further part: it has no afterstates and no kernel steps it
+constexpr int kPieceDead = 0xFF;      // game over without reset (rollout forks: return -1, game.py:138-145), or a
+                                      // terminal board imported from the host
+constexpr int kPieceVoid = 0xFE;      // fork of an illegal / non-existent action; an id that names no piece
+struct F8 { float v[8]; };            // eight per-feature floats (directions, policy weights) passed by value
 
 // Orientation descriptor, one 32-bit word:
 //   [0:3)  w       width in columns

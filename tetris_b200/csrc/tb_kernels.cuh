@@ -1,4 +1,4 @@
-// tb_kernels.cu -- sm_100a kernels + C ABI (include/tetris_b200.h) of the batched Tetris environment.
+// tb_kernels.cuh -- sm_100a kernel templates of the batched Tetris environment, per board shape <C, R>.
 //
 // Kernels:
 //   k_reset        K0  Tetris.__init__/reset            game.py:21-63
@@ -12,11 +12,16 @@
 // windows of envs that hold the same piece, lane = (env of the window, anchor column), so the piece's orientation
 // loop and width are warp-uniform and lanes stay busy although pieces have 9..34 placements.  Placements that
 // clear a line are rare and costly (from-scratch evaluation): they are marked in per-env bit masks and evaluated
-// 32 at a time instead of diverging the common incremental path.  K2 and the random rollout are thread per env.
-// See DESIGN.md section 3.
+// 32 at a time instead of diverging the common incremental path.  See DESIGN.md section 3.
+//
+// Build layout: this header is compiled once per board shape by tb_shape.cu (-DTB_C=.. -DTB_R=..), which exports the
+// shape's launchers as a table of function pointers (ShapeVT, tb_shape.h); tb_abi.cu holds the extern "C" entry points
+// of include/tetris_b200.h and dispatches on the shape.  One translation unit per shape keeps a rebuild at the cost of
+// its slowest shape and lets further shapes be compiled on demand (tb_load_shape).
 //
 // HBM layout: see include/tetris_b200.h (row masks, 8 rows per 128-bit word, SoA over envs -> every global
 // load/store of state is a coalesced 128-bit access).
+#pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -27,11 +32,12 @@
 
 #include "../../include/tetris_b200.h"
 #include "tb_core.cuh"
+#include "tb_shape.h"
 
 namespace tb {
 
-__constant__ uint32_t c_ori[kNumOris] = { TB_ORI_TABLE(TB_X_ORI) };
-__constant__ uint32_t c_piece[kNumPieces] = { TB_PIECE_TABLE(TB_X_PIECE) };
+static __constant__ uint32_t c_ori[kNumOris] = { TB_ORI_TABLE(TB_X_ORI) };
+static __constant__ uint32_t c_piece[kNumPieces] = { TB_PIECE_TABLE(TB_X_PIECE) };
 
 constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 
@@ -41,7 +47,6 @@ struct StateView {
     uint2 *epi;         // [n_env]
     int64_t n_env;
 };
-struct F8 { float v[8]; };
 
 template <int C, int R>
 static StateView make_view(const void *base, int64_t n_env)
@@ -60,9 +65,6 @@ static StateView make_view(const void *base, int64_t n_env)
 // device helpers
 // ---------------------------------------------------------------------------------------------
 struct Meta { int piece; uint32_t bag, draws; };
-// piece byte of an env that takes no further part in a no-reset rollout (tb_rollout_values forks)
-constexpr int kPieceDead = 0xFF;      // game over: its rollout return is -1 (game.py:138-145)
-constexpr int kPieceVoid = 0xFE;      // fork of an illegal / non-existent action
 
 __device__ __forceinline__ Meta unpack_meta(uint4 m)
 {
@@ -109,9 +111,15 @@ __device__ __forceinline__ void stage_tables(uint32_t *s_ori, uint32_t *s_piece)
     __syncthreads();
 }
 // draw the next piece of env (tape, or the env's bag RNG); returns the global piece id
+// A tape id that names no piece makes the env inert (kPieceVoid: no afterstates, never stepped) instead of indexing
+// the piece tables out of bounds.
+__device__ __forceinline__ int checked_piece(int id)
+{
+    return (id < kNumPieces || id == kPieceDead) ? id : kPieceVoid;
+}
 __device__ __forceinline__ int draw_piece(int piece_set, uint64_t key, Meta &mt, const uint8_t *tape, int64_t e)
 {
-    if (tape) { mt.draws += 1; return (int)tape[e]; }
+    if (tape) { mt.draws += 1; return checked_piece((int)tape[e]); }
     return set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
 }
 template <int C>
@@ -213,8 +221,8 @@ template <int TILE, int THREADS = TILE> struct BestSmem {
 // Compile-time images of the two shared-memory tables (tb_core.cuh: make_odesc_image / make_run_image, checked against
 // decode_ori / run_tab_entry on the CPU by tests/hostcheck), copied -- not computed -- by every CTA: with multi-wave
 // grids a CTA often handles a single tile, and building the run table in the kernel cost about 3 % of a K1 tile.
-__device__ const OdescImage g_odesc = make_odesc_image();
-template <int R> __device__ const RunImage<R> g_run = make_run_image<R>();
+static __device__ const OdescImage g_odesc = make_odesc_image();
+template <int R> static __device__ const RunImage<R> g_run = make_run_image<R>();
 
 template <int C, int R, int TILE>
 __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
@@ -454,6 +462,7 @@ k_afterstates_export(StateView sv, float *__restrict__ feats, uint16_t *__restri
     const int slot = (int)(idx % a_stride);
     if (e >= sv.n_env) return;
     const Meta mt = unpack_meta(sv.meta[e]);
+    if (mt.piece >= kNumPieces) return;                 // finished / void fork: no afterstates
     const uint32_t pw = s_piece[mt.piece];
     if (slot >= piece_num_slots(pw, C)) return;
     uint32_t col[C], nc[C];
@@ -503,25 +512,33 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
     uint2 ep = sv.epi[e];
     const bool live = mt.piece < kNumPieces;                                  // not a finished rollout fork
     const uint32_t pw = s_piece[live ? mt.piece : 0];
-    const int n_slots = piece_num_slots(pw, C);
     const int action = actions[e];
+    const unsigned long long vm = live ? valid_mask<C, R>(col, pw, s_ori) : 0ull;   // game.py:69
     int sel = -1;
-    if (action >= 0 && live) {
+    if (action >= 0) {
         if (flags & TB_FLAG_ACTION_IS_SLOT) {
-            if (action < n_slots) {
-                int ori, c;
-                slot_to_placement(pw, C, action, ori, c);
-                if (placement_valid<C, R>(col, s_ori[ori], c, max_height<C>(col))) sel = action;
-            }
-        } else {
-            const unsigned long long vm = valid_mask<C, R>(col, pw, s_ori);   // game.py:69
-            if (action < __popcll(vm)) sel = nth_set_bit(vm, action);         // game.py:83
+            if (action < 64 && ((vm >> action) & 1ull)) sel = action;
+        } else if (action < __popcll(vm)) {
+            sel = nth_set_bit(vm, action);                                    // game.py:83
         }
     }
-    if (sel < 0) {                                                            // IndexError in the reference
-        if (status) atomicOr(status, 1);
+    if (sel < 0) {
+        // IndexError in the reference (game.py:83).  The env is left untouched, its outputs are defined (zero
+        // observation / reward / lines; done = it has no legal placement at all), and status reports the lowest
+        // offending env as 0x7FFFFFFF - env.
+        if (status) atomicMax(status, 0x7FFFFFFF - (int)(e < 0x7FFFFFFE ? e : 0x7FFFFFFE));
+        if (!(flags & TB_FLAG_VALIDATE_ONLY)) {
+            if (obs) {
+                float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
+                o[0] = make_float4(0.f, 0.f, 0.f, 0.f); o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (reward) reward[e] = 0;
+            if (done) done[e] = (uint8_t)(vm == 0ull);
+            if (lines) lines[e] = 0;
+        }
         return;
     }
+    if (flags & TB_FLAG_VALIDATE_ONLY) return;                                // dry run: only the status is produced
     int ori, c;
     slot_to_placement(pw, C, sel, ori, c);
     Eval ev;
@@ -530,7 +547,7 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
     int rew = lc - 1;                                                         // game.py:86
     const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
     mt.piece = draw_piece(piece_set, key, mt, tape, e);                       // game.py:87
-    const bool dn = !any_valid<C, R>(col, s_piece[mt.piece], s_ori);          // game.py:88,94-100
+    const bool dn = mt.piece >= kNumPieces || !any_valid<C, R>(col, s_piece[mt.piece], s_ori);   // game.py:88,94-100
     if (dn) rew -= 100;                                                       // game.py:89-90
     ep.x += 1u; ep.y += (uint32_t)lc;
     if (obs) {
@@ -615,15 +632,16 @@ __device__ __forceinline__ void stats_flush(const LaneStats &s, long long *s_blk
 template <int C, int R>
 __device__ __forceinline__ unsigned long long
 apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece_set, uint64_t key,
-                const uint32_t *s_ori, const uint32_t *s_piece, LaneStats &st, bool no_reset = false)
+                const uint32_t *s_ori, const uint32_t *s_piece, LaneStats &st, bool no_reset = false,
+                const uint8_t *tape_piece = nullptr)
 {
     int a, term;
     uint32_t full;
     place_and_clear<C, R>(col, d, c, a, full, term);
     const int lc = popc32(full);
     int rew = lc - 1;
-    mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
-    unsigned long long vm = valid_mask<C, R>(col, s_piece[mt.piece], s_ori);
+    mt.piece = draw_piece(piece_set, key, mt, tape_piece, 0);
+    unsigned long long vm = mt.piece < kNumPieces ? valid_mask<C, R>(col, s_piece[mt.piece], s_ori) : 0ull;
     const bool dn = vm == 0ull;
     if (dn) rew -= 100;
     ep.x += 1u; ep.y += (uint32_t)lc;
@@ -648,7 +666,7 @@ apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece
 template <int C, int R>
 __global__ void __launch_bounds__(128, 6)                  // 80 registers, no spills (measured: profiles/README.md, r1g)
 k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, int64_t *stats,
-                 int no_reset)
+                 int no_reset, const uint8_t *__restrict__ tape, int tape_stride)
 {
     __shared__ uint32_t s_ori[32], s_piece[16];
     __shared__ long long s_blk[TB_ST_COUNT];
@@ -681,7 +699,8 @@ k_rollout_random(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             const int slot = nth_set_bit(vm, action);
             int ori, c;
             slot_to_placement(pw, C, slot, ori, c);
-            vm = apply_placement<C, R>(col, mt, ep, s_ori[ori], c, piece_set, key, s_ori, s_piece, st, no_reset != 0);
+            vm = apply_placement<C, R>(col, mt, ep, s_ori[ori], c, piece_set, key, s_ori, s_piece, st, no_reset != 0,
+                                       tape ? tape + e * tape_stride + t : nullptr);
         }
         store_board<C, R>(sv, e, col);
         sv.meta[e] = pack_meta<C>(col, mt);
@@ -709,7 +728,7 @@ __device__ __forceinline__ unsigned long long score_key(uint32_t ord, int slot)
 template <int C, int R, int TILE, int MINB, int THREADS = TILE>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats,
-                 int no_reset)
+                 int no_reset, const uint8_t *__restrict__ tape, int tape_stride)
 {
     using K = Env<C, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -872,8 +891,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     place_and_clear<C, R>(col, sm.ori[ori], cc, a, full, term);
                     lc = popc32(full);
                     placed = true;
-                    mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
-                    dn = !any_valid<C, R>(col, sm.piece[mt.piece], sm.ori);
+                    mt.piece = draw_piece(piece_set, key, mt, tape ? tape + e * tape_stride + t : nullptr, 0);
+                    dn = mt.piece >= kNumPieces || !any_valid<C, R>(col, sm.piece[mt.piece], sm.ori);
                     ep.x += 1u; ep.y += (uint32_t)lc;
                     ep_done = ep;
                 }
@@ -944,7 +963,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
 // ---------------------------------------------------------------------------------------------
 template <int C, int R>
 __global__ void __launch_bounds__(128)
-k_fork(StateView parent, StateView child, int a_stride, int n_forks, uint64_t seed2, int64_t child_offset, int piece_set)
+k_fork(StateView parent, StateView child, int a_stride, int n_forks, uint64_t seed2, int64_t child_offset, int piece_set,
+       const uint8_t *__restrict__ tape, int tape_stride)
 {
     __shared__ uint32_t s_ori[32], s_piece[16];
     stage_tables(s_ori, s_piece);
@@ -974,38 +994,12 @@ k_fork(StateView parent, StateView child, int a_stride, int n_forks, uint64_t se
         uint32_t full;
         place_and_clear<C, R>(col, s_ori[ori], c, a, full, term);          // self.step(action): game.py:83
         const uint64_t key = env_key(seed2, (uint64_t)(child_offset + d));
-        mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));   // :87
-        if (!any_valid<C, R>(col, s_piece[mt.piece], s_ori)) mt.piece = kPieceDead;              // :88, :133-137
+        mt.piece = draw_piece(piece_set, key, mt, tape ? tape + d * tape_stride : nullptr, 0);   // :87
+        if (mt.piece < kNumPieces && !any_valid<C, R>(col, s_piece[mt.piece], s_ori)) mt.piece = kPieceDead;   // :88, :133-137
     }
     store_board<C, R>(child, d, col);
     child.meta[d] = pack_meta<C>(col, mt);
     child.epi[d] = make_uint2(0u, 0u);
-}
-
-// Sum of the rollout returns of an (env, action)'s forks: -1 for a fork that ended (game.py:134,143-145), else the
-// lines cleared minus the placements made after the first step (reward = lines - 1 per step, game.py:86,141).
-__global__ void k_fork_returns(const uint4 *__restrict__ meta, const uint2 *__restrict__ epi, int64_t n_parent,
-                               int a_stride, int n_forks, int32_t *__restrict__ ret_sum,
-                               unsigned long long *__restrict__ valid)
-{
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_parent) return;
-    unsigned long long vm = 0ull;
-    for (int s = 0; s < a_stride; ++s) {
-        int sum = 0;
-        bool legal = false;
-        for (int f = 0; f < n_forks; ++f) {
-            const int64_t d = (e * a_stride + s) * n_forks + f;
-            const int piece = (int)((meta[d].z >> 16) & 0xffu);
-            if (piece == kPieceVoid) continue;
-            legal = true;
-            const uint2 ep = epi[d];
-            sum += piece == kPieceDead ? -1 : (int)ep.y - (int)ep.x;
-        }
-        ret_sum[e * a_stride + s] = sum;
-        if (legal && s < 64) vm |= 1ull << s;
-    }
-    if (valid) valid[e] = vm;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1059,7 +1053,10 @@ __global__ void k_import(StateView sv, int64_t first, int64_t count, const uint1
     for (int b = 0; b < S::NB; ++b)
         sv.planes[(int64_t)b * sv.n_env + e] = make_uint4(w[4 * b], w[4 * b + 1], w[4 * b + 2], w[4 * b + 3]);
     Meta mt = unpack_meta(sv.meta[e]);
-    if (piece_in) mt.piece = piece_in[i];
+    if (piece_in) mt.piece = checked_piece((int)piece_in[i]);
+    // a board with a cell at or above row R is a terminal state (state.py:111-117): nothing is placed on it any more
+    // (every kernel relies on column heights <= R)
+    if (max_height<C>(col) > R && mt.piece < kNumPieces) mt.piece = kPieceDead;
     sv.meta[e] = pack_meta<C>(col, mt);
 }
 
@@ -1105,114 +1102,24 @@ __global__ void k_eval_states(int64_t n, const uint16_t *__restrict__ rows_in, c
     }
 }
 
-// Tetris.fitness (game.py:109-120) of n feature rows
-__global__ void k_fitness(int64_t n, const float *__restrict__ feats, F8 wts, float *__restrict__ out)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 a = reinterpret_cast<const float4 *>(feats)[2 * i], b = reinterpret_cast<const float4 *>(feats)[2 * i + 1];
-    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    out[i] = fitness(f, wts.v);
-}
-
-// Softmax policy over the legal afterstates of every env (utils.py:26-31 compute_action_probabilities) and the
-// gradient of the log-probability of the chosen action (utils.py:35-38), float64 like the reference's NumPy.
-// One thread per env; utilities are recomputed instead of stored (A <= 36 rows of 8 floats, L1/L2 resident).
-struct D8 { double v[8]; };
-__device__ __forceinline__ double utility(const float *__restrict__ row, const D8 &w, double inv_t)
-{
-    const float4 a = reinterpret_cast<const float4 *>(row)[0], b = reinterpret_cast<const float4 *>(row)[1];
-    double u = (double)a.x * w.v[0];
-    u += (double)a.y * w.v[1]; u += (double)a.z * w.v[2]; u += (double)a.w * w.v[3];
-    u += (double)b.x * w.v[4]; u += (double)b.y * w.v[5]; u += (double)b.z * w.v[6]; u += (double)b.w * w.v[7];
-    return u * inv_t;
-}
-__global__ void k_action_probs(int64_t n, int a_stride, const float *__restrict__ feats,
-                               const unsigned long long *__restrict__ valid, D8 w, double inv_t,
-                               const int32_t *__restrict__ actions, double *__restrict__ probs, double *__restrict__ grad)
-{
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const unsigned long long vm = valid[e];
-    const float *base = feats + (size_t)e * a_stride * 8;
-    double umax = -1.0e300;
-    for (unsigned long long m = vm; m; m &= m - 1) umax = fmax(umax, utility(base + 8 * (__ffsll((long long)m) - 1), w, inv_t));
-    double z = 0.0;
-    for (unsigned long long m = vm; m; m &= m - 1) z += exp(utility(base + 8 * (__ffsll((long long)m) - 1), w, inv_t) - umax);
-    const double inv_z = vm ? 1.0 / z : 0.0;
-    double mean[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int s = 0; s < a_stride; ++s) {
-        double p = 0.0;
-        if (s < 64 && ((vm >> s) & 1ull)) {
-            const float *row = base + 8 * s;
-            p = exp(utility(row, w, inv_t) - umax) * inv_z;
-            if (grad) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) mean[i] += p * (double)row[i];
-            }
-        }
-        if (probs) probs[(size_t)e * a_stride + s] = p;
-    }
-    if (grad) {
-        const int sel = actions ? actions[e] : -1;            // enumeration slot of the chosen action
-        const bool ok = sel >= 0 && sel < a_stride && sel < 64 && ((vm >> sel) & 1ull);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) grad[e * 8 + i] = ok ? (double)base[8 * sel + i] - mean[i] : 0.0;
-    }
-}
-
-}  // namespace tb
 
 // =============================================================================================
-// C ABI
+// Launchers of one board shape (the entries of its TbShapeVT).  Argument checks that do not depend on the shape are
+// done by the ABI layer (tb_abi.cu) before these are reached.
 // =============================================================================================
-using namespace tb;
-
-// board shapes compiled in: the three of BASELINE.json's configs plus two extras (mid-size, tiny edge case)
-#ifdef TB_ONLY_10x20   /* quick experimental builds: nvcc -DTB_ONLY_10x20 */
-#define TB_SHAPES(X) X(10, 20)
-#else
-#define TB_SHAPES(X) X(10, 20) X(10, 10) X(6, 12) X(8, 16) X(4, 4)
-#endif
-
-static thread_local char g_err[256] = "";
-static int fail(const char *fmt, const char *detail)
+static inline int launch_fail(const TbLaunchCtx *cx, const char *what, const char *detail)
 {
-    snprintf(g_err, sizeof g_err, fmt, detail);
-    return -1;
+    if (cx->err && cx->err_len) snprintf(cx->err, cx->err_len, "%s: %s", what, detail);
+    return -2;
 }
-static int check_launch(const char *what)
+static inline int check_launch(const TbLaunchCtx *cx, const char *what)
 {
     const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
-        return -2;
-    }
-    return 0;
-}
-static int sm_count()
-{
-    static thread_local int cached_dev = -1, cached = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != cached_dev) {
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        cached_dev = dev;
-    }
-    return cached > 0 ? cached : 148;
-}
-// Tuning knobs read from the environment (experiments only; the defaults are what ships and what is tested):
-//   TB_K1_CFG  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5
-//   TB_K3_CFG  0: 256 x 2 (default)   2: 128 x 4   3: 128 x 5
-//   both       4: 32 envs x 128 threads   5: 64 envs x 256 threads   (several warps per 32-env group, small batches)
-static int tuning_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
+    return e == cudaSuccess ? 0 : launch_fail(cx, what, cudaGetErrorString(e));
 }
 // dynamic shared memory above 48 KB is opt-in per kernel
 // (done once per kernel and device: the driver call costs a microsecond or two, which small-batch loops would pay per launch)
-static int opt_in_smem(const void *kernel, size_t bytes)
+static inline int opt_in_smem(const TbLaunchCtx *cx, const void *kernel, size_t bytes)
 {
     static std::mutex mu;
     static const void *seen_kernel[256];
@@ -1225,10 +1132,7 @@ static int opt_in_smem(const void *kernel, size_t bytes)
             if (seen_kernel[i] == kernel && seen_dev[i] == dev) return 0;
     }
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) {
-        snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(shared memory %zu B): %s", bytes, cudaGetErrorString(e));
-        return -2;
-    }
+    if (e != cudaSuccess) return launch_fail(cx, "cudaFuncSetAttribute(shared memory)", cudaGetErrorString(e));
     std::lock_guard<std::mutex> lock(mu);
     if (n_seen < 256) { seen_kernel[n_seen] = kernel; seen_dev[n_seen] = dev; ++n_seen; }
     return 0;
@@ -1236,337 +1140,159 @@ static int opt_in_smem(const void *kernel, size_t bytes)
 // Grid of a kernel that loops over its work items: `waves` x (SMs x resident CTAs per SM).  waves = 1 is a strictly
 // persistent grid; the tile kernels use 8 (K1) / 16 (K3) -- tiles and envs differ in cost, and handing the hardware
 // scheduler more, shorter CTAs evens the SMs out (K1 -4 %, K3 -2.7 %, random rollout -17 % against waves = 1) at the
-// price of a few more table set-ups per SM.
-static unsigned grid_for(int64_t work_items, int per_block, int blocks_per_sm, int waves = 1)
+// price of a few more table set-ups per SM.  cx->max_ctas (tests only) caps the grid so that every CTA takes several tiles.
+static inline unsigned grid_for(const TbLaunchCtx *cx, int64_t work_items, int per_block, int blocks_per_sm, int waves = 1)
 {
     const int64_t need = (work_items + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)sm_count() * blocks_per_sm * waves;   // a multiple of the SM count
+    int64_t cap = (int64_t)cx->sm_count * blocks_per_sm * waves;        // a multiple of the SM count
+    if (cx->max_ctas > 0 && cx->max_ctas < cap) cap = cx->max_ctas;
     return (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 // Tile configuration by batch size: the throughput configuration (cfg 0, 256-env tiles, thread per env) once there is
-// at least one tile per SM; below that 128-env tiles (`mid`); and for batches of at most TB_SMALL_GROUPS (default 4)
+// at least one tile per SM; below that 128-env tiles (`mid`); and for batches of at most cx->small_groups (default 4)
 // 32-env groups per SM the small-batch configuration 4 (32 envs and 4 warps per CTA: shortest critical path).
-static int small_batch_cfg(int64_t n_env, int mid)
+//   K1 cfg  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5
+//   K3 cfg  0: 256 x 2 (default)   2: 128 x 4   3: 128 x 5
+//   both    4: 32 envs x 128 threads   5: 64 envs x 256 threads   (several warps per 32-env group, small batches)
+static inline int small_batch_cfg(const TbLaunchCtx *cx, int64_t n_env, int mid)
 {
-    const int sms = sm_count();
-    if ((n_env + 31) / 32 <= (int64_t)tuning_int("TB_SMALL_GROUPS", 4) * sms) return 4;
-    return (n_env + 255) / 256 < sms ? mid : 0;
+    if ((n_env + 31) / 32 <= (int64_t)cx->small_groups * cx->sm_count) return 4;
+    return (n_env + 255) / 256 < cx->sm_count ? mid : 0;
 }
-static F8 f8_from(const float *p, float dflt)
+static inline F8 f8_from(const float *p, float dflt)
 {
     F8 r;
     for (int i = 0; i < 8; ++i) r.v[i] = p ? p[i] : dflt;
     return r;
 }
 
-extern "C" {
+template <int C, int R>
+struct ShapeOps {
+    using S = Shape<C, R>;
+    static StateView view(const void *base, int64_t n_env) { return make_view<C, R>(base, n_env); }
 
-int tb_version(void) { return TB_VERSION; }
-const char *tb_last_error(void) { return g_err; }
-
-int tb_supported_shape(int C, int R)
-{
-#define X(c, r) if (C == c && R == r) return 1;
-    TB_SHAPES(X)
-#undef X
-    return 0;
-}
-
-size_t tb_state_bytes(int C, int R, int64_t n_env)
-{
-#define X(c, r) if (C == c && R == r) return (size_t)n_env * (size_t)(16 * (Shape<c, r>::NB + 1) + 8);
-    TB_SHAPES(X)
-#undef X
-    return 0;
-}
-
-int tb_num_slots(int piece, int C)
-{
-    if (piece < 0 || piece >= kNumPieces) return 0;
-    return piece_num_slots(kPieceHost[piece], C);
-}
-
-int tb_a_max(int C, int piece_set)
-{
-    int m = 0;
-    for (int i = 0; i < set_size(piece_set); ++i) {
-        const int n = tb_num_slots(set_piece(piece_set, i), C);
-        if (n > m) m = n;
+    static int reset(const TbLaunchCtx *cx, void *state, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
+                     const uint8_t *tape, const uint8_t *mask)
+    {
+        k_reset<C, R><<<(unsigned)((n_env + 255) / 256), 256, 0, (cudaStream_t)cx->stream>>>(
+            view(state, n_env), env_offset, seed, piece_set, tape, mask);
+        return check_launch(cx, "tb_reset");
     }
-    return m;
-}
 
-int tb_slot_info(int piece, int C, int slot, int32_t *out)
-{
-    if (piece < 0 || piece >= kNumPieces || !out) return fail("%s: bad piece or null output", __func__);
-    const uint32_t pw = kPieceHost[piece];
-    if (C < 4 || slot < 0 || slot >= piece_num_slots(pw, C)) return fail("%s: slot out of range", __func__);
-    int ori, c;
-    slot_to_placement(pw, C, slot, ori, c);
-    const uint32_t d = kOriHost[ori];
-    int n = 0;
-    for (int i = 0; i < 17; ++i) out[i] = 0;
-    out[0] = c; out[1] = desc_w(d); out[3] = desc_chg(d); out[4] = desc_bonus2(d);
-    for (int dx = 0; dx < 4; ++dx)
-        for (int k = 0; k < desc_len(d, dx); ++k) {
-            const int dy = desc_bot(d, dx) + k;
-            out[9 + 2 * n] = dx; out[10 + 2 * n] = dy;
-            if (dy < desc_chg(d)) out[5 + dy] += 1;                 // pieces_per_changed_row
-            ++n;
+    static int afterstates(const TbLaunchCtx *cx, const void *state, int64_t n_env, void *feats_out, uint64_t *valid_out,
+                           int32_t *count_out, int a_stride, const float *directions, int flags)
+    {
+        typedef void (*kern_t)(StateView, float *, unsigned long long *, int *, int, F8, int);
+        const F8 dirs = f8_from(directions, 1.0f);
+        // small batches (fewer 256-env tiles than SMs) use 128-env tiles: twice the CTAs, half the per-tile latency
+        const int cfg = cx->k1_cfg >= 0 ? cx->k1_cfg : small_batch_cfg(cx, n_env, 3);
+        kern_t kern; size_t smem; int tile, minb, threads = 0;
+        if (cfg == 4) { tile = 32; threads = 128; minb = 4; smem = sizeof(CtaSmem<C, R, 32>);
+            kern = directions ? k_afterstates<C, R, true, 32, 4, 128> : k_afterstates<C, R, false, 32, 4, 128>; }
+        else if (cfg == 5) { tile = 64; threads = 256; minb = 2; smem = sizeof(CtaSmem<C, R, 64>);
+            kern = directions ? k_afterstates<C, R, true, 64, 2, 256> : k_afterstates<C, R, false, 64, 2, 256>; }
+        else if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<C, R, 128>);
+            kern = directions ? k_afterstates<C, R, true, 128, 5> : k_afterstates<C, R, false, 128, 5>; }
+        else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<C, R, 256>);
+            kern = directions ? k_afterstates<C, R, true, 256, 2> : k_afterstates<C, R, false, 256, 2>; }
+        else { tile = 256; minb = 3; smem = sizeof(CtaSmem<C, R, 256>);
+            kern = directions ? k_afterstates<C, R, true, 256, 3> : k_afterstates<C, R, false, 256, 3>; }
+        if (opt_in_smem(cx, (const void *)kern, smem)) return -2;
+        kern<<<grid_for(cx, n_env, tile, minb, 8), threads ? threads : tile, smem, (cudaStream_t)cx->stream>>>(
+            view(state, n_env), (float *)feats_out, (unsigned long long *)valid_out, count_out, a_stride, dirs, flags);
+        return check_launch(cx, "tb_afterstates");
+    }
+
+    static int afterstates_export(const TbLaunchCtx *cx, const void *state, int64_t n_env, float *feats_out,
+                                  uint16_t *rows_out, uint8_t *heights_out, int32_t *info_out, int a_stride)
+    {
+        const int64_t total = n_env * a_stride;
+        k_afterstates_export<C, R><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)cx->stream>>>(
+            view(state, n_env), feats_out, rows_out, heights_out, info_out, a_stride);
+        return check_launch(cx, "tb_afterstates_export");
+    }
+
+    static int step(const TbLaunchCtx *cx, void *state, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
+                    const int32_t *actions, const uint8_t *tape, float *obs, int32_t *reward, uint8_t *done,
+                    int32_t *lines, int32_t *status, int flags)
+    {
+        k_step<C, R><<<(unsigned)((n_env + 127) / 128), 128, 0, (cudaStream_t)cx->stream>>>(
+            view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags,
+            f8_from(nullptr, 1.0f));
+        return check_launch(cx, "tb_step");
+    }
+
+    static int rollout(const TbLaunchCtx *cx, void *state, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
+                       int n_steps, int policy, const float *weights, int64_t *stats, int no_reset, const uint8_t *tape,
+                       int tape_stride)
+    {
+        cudaStream_t st = (cudaStream_t)cx->stream;
+        if (policy == TB_POLICY_RANDOM) {
+            k_rollout_random<C, R><<<grid_for(cx, n_env, 128, 6, 5), 128, 0, st>>>(
+                view(state, n_env), env_offset, seed, piece_set, n_steps, stats, no_reset, tape, tape_stride);
+            return check_launch(cx, "tb_rollout");
         }
-    out[2] = n;
-    return 0;
-}
-
-#define TB_CHECK_COMMON()                                                                   \
-    if (n_env <= 0) return fail("%s: n_env must be positive", __func__);                   \
-    if (!tb_supported_shape(C, R)) return fail("%s: unsupported board shape", __func__);
-
-int tb_reset(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
-             const uint8_t *piece_tape, const uint8_t *reset_mask, void *stream)
-{
-    TB_CHECK_COMMON();
-    if (piece_set < 0 || piece_set > 1) return fail("%s: piece_set must be 0 or 1", __func__);
-    cudaStream_t st = (cudaStream_t)stream;
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        k_reset<c, r><<<(unsigned)((n_env + 255) / 256), 256, 0, st>>>(make_view<c, r>(state, n_env),    \
-            env_offset, seed, piece_set, piece_tape, reset_mask);                                        \
-        return check_launch("tb_reset");                                                                 \
+        typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int, const uint8_t *, int);
+        kern_t kern; size_t smem; int tile, minb, threads = 0;
+        const int cfg = cx->k3_cfg >= 0 ? cx->k3_cfg : small_batch_cfg(cx, n_env, 2);
+        if (cfg == 4) { tile = 32; threads = 128; minb = 4; kern = k_rollout_greedy<C, R, 32, 4, 128>;
+            smem = ((sizeof(CtaSmem<C, R, 32>) + 15) & ~(size_t)15) + sizeof(BestSmem<32, 128>); }
+        else if (cfg == 5) { tile = 64; threads = 256; minb = 2; kern = k_rollout_greedy<C, R, 64, 2, 256>;
+            smem = ((sizeof(CtaSmem<C, R, 64>) + 15) & ~(size_t)15) + sizeof(BestSmem<64, 256>); }
+        else if (cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<C, R, 128, 5>;
+            smem = ((sizeof(CtaSmem<C, R, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }
+        else if (cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<C, R, 128, 4>;
+            smem = ((sizeof(CtaSmem<C, R, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }
+        else { tile = 256; minb = 2; kern = k_rollout_greedy<C, R, 256, 2>;
+            smem = ((sizeof(CtaSmem<C, R, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }
+        if (opt_in_smem(cx, (const void *)kern, smem)) return -2;
+        kern<<<grid_for(cx, n_env, tile, minb, 16), threads ? threads : tile, smem, st>>>(
+            view(state, n_env), env_offset, seed, piece_set, n_steps, f8_from(weights, 0.0f), stats, no_reset, tape,
+            tape_stride);
+        return check_launch(cx, "tb_rollout");
     }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
 
-int tb_afterstates(const void *state, int C, int R, int64_t n_env, float *feats_out, uint64_t *valid_out,
-                   int32_t *count_out, int a_stride, const float *directions, int flags, void *stream)
-{
-    TB_CHECK_COMMON();
-    if (!feats_out) return fail("%s: feats_out is required", __func__);
-    if (a_stride < 1) return fail("%s: a_stride must be >= the piece set's slot count", __func__);
-    cudaStream_t st = (cudaStream_t)stream;
-    const F8 dirs = f8_from(directions, 1.0f);
-    // small batches (fewer 256-env tiles than SMs) use 128-env tiles: twice the CTAs, half the per-tile latency
-    const int cfg = tuning_int("TB_K1_CFG", small_batch_cfg(n_env, 3));
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        typedef void (*kern_t)(StateView, float *, unsigned long long *, int *, int, F8, int);           \
-        kern_t kern; size_t smem; int tile, minb, threads = 0;                                           \
-        if (cfg == 4) { tile = 32; threads = 128; minb = 4; smem = sizeof(CtaSmem<c, r, 32>);            \
-            kern = directions ? k_afterstates<c, r, true, 32, 4, 128> : k_afterstates<c, r, false, 32, 4, 128>; }\
-        else if (cfg == 5) { tile = 64; threads = 256; minb = 2; smem = sizeof(CtaSmem<c, r, 64>);       \
-            kern = directions ? k_afterstates<c, r, true, 64, 2, 256> : k_afterstates<c, r, false, 64, 2, 256>; }\
-        else if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<c, r, 128>);                    \
-            kern = directions ? k_afterstates<c, r, true, 128, 5> : k_afterstates<c, r, false, 128, 5>; }\
-        else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<c, r, 256>);                    \
-            kern = directions ? k_afterstates<c, r, true, 256, 2> : k_afterstates<c, r, false, 256, 2>; }\
-        else { tile = 256; minb = 3; smem = sizeof(CtaSmem<c, r, 256>);                                  \
-            kern = directions ? k_afterstates<c, r, true, 256, 3> : k_afterstates<c, r, false, 256, 3>; }\
-        if (opt_in_smem((const void *)kern, smem)) return -2;                                            \
-        kern<<<grid_for(n_env, tile, minb, 8), threads ? threads : tile, smem, st>>>(make_view<c, r>(state, n_env), feats_out,  \
-            (unsigned long long *)valid_out, count_out, a_stride, dirs, flags);                          \
-        return check_launch("tb_afterstates");                                                           \
+    static int fork(const TbLaunchCtx *cx, const void *parent, int64_t n_env, void *child, int a_stride, int n_forks,
+                    uint64_t seed2, int64_t child_offset, int piece_set, const uint8_t *tape, int tape_stride)
+    {
+        const int64_t n_child = n_env * a_stride * n_forks;
+        k_fork<C, R><<<(unsigned)((n_child + 127) / 128), 128, 0, (cudaStream_t)cx->stream>>>(
+            view(parent, n_env), view(child, n_child), a_stride, n_forks, seed2, child_offset, piece_set, tape, tape_stride);
+        return check_launch(cx, "tb_rollout_values(fork)");
     }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
 
-int tb_afterstates_export(const void *state, int C, int R, int64_t n_env, float *feats_out, uint16_t *rows_out,
-                          uint8_t *heights_out, int32_t *info_out, int a_stride, void *stream)
-{
-    TB_CHECK_COMMON();
-    if (a_stride < 1) return fail("%s: a_stride must be >= the piece set's slot count", __func__);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t total = n_env * a_stride;
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        k_afterstates_export<c, r><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(                     \
-            make_view<c, r>(state, n_env), feats_out, rows_out, heights_out, info_out, a_stride);        \
-        return check_launch("tb_afterstates_export");                                                    \
+    static int export_boards(const TbLaunchCtx *cx, const void *state, int64_t n_env, int64_t first, int64_t count,
+                             uint16_t *rows_out, uint8_t *heights_out, uint8_t *piece_out)
+    {
+        k_export<C, R><<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)cx->stream>>>(
+            view(state, n_env), first, count, rows_out, heights_out, piece_out);
+        return check_launch(cx, "tb_export_boards");
     }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
 
-int tb_step(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
-            const int32_t *actions, const uint8_t *piece_tape, float *obs_out, int32_t *reward_out, uint8_t *done_out,
-            int32_t *lines_out, int32_t *status_out, int flags, void *stream)
-{
-    TB_CHECK_COMMON();
-    if (!actions) return fail("%s: actions is required", __func__);
-    if (piece_set < 0 || piece_set > 1) return fail("%s: piece_set must be 0 or 1", __func__);
-    cudaStream_t st = (cudaStream_t)stream;
-    const F8 dirs = f8_from(nullptr, 1.0f);
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        k_step<c, r><<<(unsigned)((n_env + 127) / 128), 128, 0, st>>>(make_view<c, r>(state, n_env),     \
-            env_offset, seed, piece_set, actions, piece_tape, obs_out, reward_out, done_out, lines_out,  \
-            status_out, flags, dirs);                                                                    \
-        return check_launch("tb_step");                                                                  \
+    static int import_boards(const TbLaunchCtx *cx, void *state, int64_t n_env, int64_t first, int64_t count,
+                             const uint16_t *rows_in, const uint8_t *piece_in)
+    {
+        k_import<C, R><<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)cx->stream>>>(
+            view(state, n_env), first, count, rows_in, piece_in);
+        return check_launch(cx, "tb_import_boards");
     }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
 
-static int rollout_impl(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
-                        int n_steps, int policy, const float *weights, int64_t *stats, void *stream, int no_reset)
-{
-    TB_CHECK_COMMON();
-    if (!stats) return fail("%s: stats is required", __func__);
-    if (n_steps < 0) return fail("%s: n_steps must be >= 0", __func__);
-    if (piece_set < 0 || piece_set > 1) return fail("%s: piece_set must be 0 or 1", __func__);
-    if (policy == TB_POLICY_GREEDY && !weights) return fail("%s: greedy policy needs weights", __func__);
-    if (policy != TB_POLICY_GREEDY && policy != TB_POLICY_RANDOM) return fail("%s: unknown policy", __func__);
-    cudaStream_t st = (cudaStream_t)stream;
-    const F8 wts = f8_from(weights, 0.0f);
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        if (policy == TB_POLICY_RANDOM)                                                                  \
-            k_rollout_random<c, r><<<grid_for(n_env, 128, 6, 5), 128, 0, st>>>(make_view<c, r>(state, n_env), \
-                env_offset, seed, piece_set, n_steps, stats, no_reset);                                  \
-        else {                                                                                           \
-            typedef void (*kern_t)(StateView, int64_t, uint64_t, int, int, F8, int64_t *, int);          \
-            kern_t kern; size_t smem; int tile, minb, threads = 0;                                       \
-            const int k3cfg = tuning_int("TB_K3_CFG", small_batch_cfg(n_env, 2));                        \
-            if (k3cfg == 4) { tile = 32; threads = 128; minb = 4; kern = k_rollout_greedy<c, r, 32, 4, 128>; \
-                smem = ((sizeof(CtaSmem<c, r, 32>) + 15) & ~(size_t)15) + sizeof(BestSmem<32, 128>); }   \
-            else if (k3cfg == 5) { tile = 64; threads = 256; minb = 2; kern = k_rollout_greedy<c, r, 64, 2, 256>; \
-                smem = ((sizeof(CtaSmem<c, r, 64>) + 15) & ~(size_t)15) + sizeof(BestSmem<64, 256>); }   \
-            else if (k3cfg == 3) { tile = 128; minb = 5; kern = k_rollout_greedy<c, r, 128, 5>;          \
-                smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
-            else if (k3cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<c, r, 128, 4>;          \
-                smem = ((sizeof(CtaSmem<c, r, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }      \
-            else { tile = 256; minb = 2; kern = k_rollout_greedy<c, r, 256, 2>;                          \
-                smem = ((sizeof(CtaSmem<c, r, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }      \
-            if (opt_in_smem((const void *)kern, smem)) return -2;                                        \
-            kern<<<grid_for(n_env, tile, minb, 16), threads ? threads : tile, smem, st>>>(               \
-                make_view<c, r>(state, n_env), env_offset, seed, piece_set, n_steps, wts, stats, no_reset); \
-        }                                                                                                \
-        return check_launch("tb_rollout");                                                               \
+    static int eval_states(const TbLaunchCtx *cx, int64_t n, const uint16_t *rows_in, const int32_t *params,
+                           uint16_t *rows_out, uint8_t *heights_out, int32_t *info_out, float *feats_out)
+    {
+        k_eval_states<C, R><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cx->stream>>>(
+            n, rows_in, params, rows_out, heights_out, info_out, feats_out);
+        return check_launch(cx, "tb_eval_states");
     }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
 
-int tb_rollout(void *state, int C, int R, int64_t n_env, int64_t env_offset, uint64_t seed, int piece_set,
-               int n_steps, int policy, const float *weights, int64_t *stats, void *stream)
-{
-    return rollout_impl(state, C, R, n_env, env_offset, seed, piece_set, n_steps, policy, weights, stats, stream, 0);
-}
-
-int tb_rollout_values(const void *state, int C, int R, int64_t n_env, int piece_set, void *child_state, int a_stride,
-                      int n_forks, int length, int policy, const float *weights, uint64_t seed2, int64_t child_offset,
-                      int32_t *ret_sum, uint64_t *valid_out, int64_t *stats, void *stream)
-{
-    TB_CHECK_COMMON();
-    if (!child_state || !ret_sum || !stats) return fail("%s: child_state, ret_sum and stats are required", __func__);
-    if (a_stride < 1 || a_stride > 64 || n_forks < 1 || length < 1) return fail("%s: bad a_stride / n_forks / length", __func__);
-    if (piece_set < 0 || piece_set > 1) return fail("%s: piece_set must be 0 or 1", __func__);
-    const int64_t n_child = n_env * a_stride * n_forks;
-    cudaStream_t st = (cudaStream_t)stream;
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        k_fork<c, r><<<(unsigned)((n_child + 127) / 128), 128, 0, st>>>(make_view<c, r>(state, n_env),   \
-            make_view<c, r>(child_state, n_child), a_stride, n_forks, seed2, child_offset, piece_set);   \
-        if (check_launch("tb_rollout_values(fork)")) return -2;                                          \
-        if (length > 1) {                                                                                \
-            const int rc = rollout_impl(child_state, c, r, n_child, child_offset, seed2, piece_set, length - 1, policy, \
-                                        weights, stats, stream, 1);                                      \
-            if (rc) return rc;                                                                           \
-        }                                                                                                \
-        const StateView cv = make_view<c, r>(child_state, n_child);                                      \
-        k_fork_returns<<<(unsigned)((n_env + 127) / 128), 128, 0, st>>>(cv.meta, cv.epi, n_env, a_stride, n_forks, \
-            ret_sum, (unsigned long long *)valid_out);                                                   \
-        return check_launch("tb_rollout_values(reduce)");                                                \
+    static const TbShapeVT *vt()
+    {
+        static const TbShapeVT t = {
+            TB_SHAPE_ABI, C, R, (size_t)(16 * (S::NB + 1) + 8),
+            &reset, &afterstates, &afterstates_export, &step, &rollout, &fork, &export_boards, &import_boards, &eval_states,
+        };
+        return &t;
     }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
+};
 
-int tb_export_boards(const void *state, int C, int R, int64_t n_env, int64_t first, int64_t count,
-                     uint16_t *rows_out, uint8_t *heights_out, uint8_t *piece_out, void *stream)
-{
-    TB_CHECK_COMMON();
-    if (first < 0 || count < 0 || first + count > n_env) return fail("%s: env range out of bounds", __func__);
-    if (count == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        k_export<c, r><<<(unsigned)((count + 127) / 128), 128, 0, st>>>(make_view<c, r>(state, n_env),   \
-            first, count, rows_out, heights_out, piece_out);                                             \
-        return check_launch("tb_export_boards");                                                         \
-    }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
-
-int tb_import_boards(void *state, int C, int R, int64_t n_env, int64_t first, int64_t count,
-                     const uint16_t *rows_in, const uint8_t *piece_in, void *stream)
-{
-    TB_CHECK_COMMON();
-    if (first < 0 || count < 0 || first + count > n_env) return fail("%s: env range out of bounds", __func__);
-    if (!rows_in) return fail("%s: rows_in is required", __func__);
-    if (count == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        k_import<c, r><<<(unsigned)((count + 127) / 128), 128, 0, st>>>(make_view<c, r>(state, n_env),   \
-            first, count, rows_in, piece_in);                                                            \
-        return check_launch("tb_import_boards");                                                         \
-    }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
-
-int tb_eval_states(int C, int R, int64_t n, const uint16_t *rows_in, const int32_t *params, uint16_t *rows_out,
-                   uint8_t *heights_out, int32_t *info_out, float *feats_out, void *stream)
-{
-    if (n <= 0) return fail("%s: n must be positive", __func__);
-    if (!tb_supported_shape(C, R)) return fail("%s: unsupported board shape", __func__);
-    if (!rows_in) return fail("%s: rows_in is required", __func__);
-    cudaStream_t st = (cudaStream_t)stream;
-#define X(c, r)                                                                                          \
-    if (C == c && R == r) {                                                                              \
-        k_eval_states<c, r><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, rows_in, params, rows_out,   \
-            heights_out, info_out, feats_out);                                                           \
-        return check_launch("tb_eval_states");                                                           \
-    }
-    TB_SHAPES(X)
-#undef X
-    return -1;
-}
-
-int tb_fitness(int64_t n, const float *feats, const float *weights, float *out, void *stream)
-{
-    if (n <= 0) return fail("%s: n must be positive", __func__);
-    if (!feats || !weights || !out) return fail("%s: null argument", __func__);
-    if ((reinterpret_cast<uintptr_t>(feats) & 15u) != 0) return fail("%s: feats must be 16-byte aligned", __func__);
-    k_fitness<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, feats, f8_from(weights, 0.0f), out);
-    return check_launch("tb_fitness");
-}
-
-int tb_action_probabilities(int64_t n_env, int a_stride, const float *feats, const uint64_t *valid,
-                            const double *weights, double temperature, const int32_t *actions, double *probs_out,
-                            double *grad_out, void *stream)
-{
-    if (n_env <= 0) return fail("%s: n_env must be positive", __func__);
-    if (!feats || !valid || !weights) return fail("%s: feats, valid and weights are required", __func__);
-    if (a_stride < 1 || a_stride > 64) return fail("%s: a_stride must be in 1..64", __func__);
-    if (!(temperature > 0.0)) return fail("%s: temperature must be positive", __func__);
-    if ((reinterpret_cast<uintptr_t>(feats) & 15u) != 0) return fail("%s: feats must be 16-byte aligned", __func__);
-    D8 w;
-    for (int i = 0; i < 8; ++i) w.v[i] = weights[i];
-    k_action_probs<<<(unsigned)((n_env + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        n_env, a_stride, feats, (const unsigned long long *)valid, w, 1.0 / temperature, actions, probs_out, grad_out);
-    return check_launch("tb_action_probabilities");
-}
-
-}  // extern "C"
+}  // namespace tb

@@ -3,7 +3,8 @@
 Envs are independent, and every env's RNG is keyed by (seed, GLOBAL env id), so a shard of a
 bigger job is just a BatchedTetris with `env_offset` set: results do not depend on the sharding.  The only
 exchange is the end-of-rollout reduction of the episode statistics -- an int64[16] vector, sums except two
-maxima -- done with torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).
+maxima -- done as one all-gather with torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests) plus a
+local combine.
 """
 import os
 
@@ -47,17 +48,32 @@ def combine_stats(parts):
     return out
 
 
-def reduce_stats(stats, group=None):
-    """All-reduce an episode-statistics vector over the process group: SUM everywhere except MAX for
-    max_ep_lines / max_ep_steps.  Returns a new tensor; integer arithmetic, so the result is exact and
-    independent of the reduction order.  No-op copy when torch.distributed is not initialised."""
+_gather_buf = {}
+
+
+def reduce_stats(stats, group=None, out=None):
+    """Reduce an episode-statistics vector over the process group: SUM everywhere except MAX for max_ep_lines /
+    max_ep_steps.  ONE collective -- an all-gather of the ranks' int64[16] vectors into a preallocated buffer --
+    followed by the local combine (tb_combine_stats, one tiny kernel on the same stream; CPU tensors, as in the gloo
+    tests, are combined on the host).  Integer arithmetic, so the result is exact and independent of the order.
+    Returns `out` (a new tensor when not given); a plain copy when torch.distributed is not initialised."""
+    import ctypes as C
     import torch.distributed as dist
-    out = stats.clone()
+    if out is None:
+        out = torch.empty_like(stats)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        out.copy_(stats)
         return out
-    idx = torch.as_tensor(_lib.STATS_MAX_FIELDS, device=out.device)
-    mx = out[idx].clone()
-    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    out[idx] = mx
+    world_size = dist.get_world_size(group)
+    key = (stats.device, world_size, stats.numel())
+    buf = _gather_buf.get(key)
+    if buf is None:
+        buf = _gather_buf[key] = torch.empty(world_size * stats.numel(), dtype=torch.int64, device=stats.device)
+    dist.all_gather_into_tensor(buf, stats.contiguous(), group=group)          # rank r's vector lands at [16 r, 16 r + 16)
+    if stats.is_cuda:
+        stream = torch.cuda.current_stream(stats.device).cuda_stream
+        _lib.check(_lib.lib().tb_combine_stats(C.c_void_p(buf.data_ptr()), world_size, C.c_void_p(out.data_ptr()),
+                                               C.c_void_p(stream)))
+    else:
+        out.copy_(combine_stats(list(buf.view(world_size, -1))))
     return out
