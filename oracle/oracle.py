@@ -62,7 +62,7 @@ def lib():
         L.orc_batch_step.restype = C.c_int
         L.orc_batch_step.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
         L.orc_batch_rollout_mt.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int]
-        L.orc_batch_rollout_values.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, u64, i64, vp, vp]
+        L.orc_batch_rollout_values.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, u64, i64, vp, vp, vp]
         L.orc_stats_count.restype = C.c_int
         _lib = L
     return _lib
@@ -211,13 +211,16 @@ class Batch:
         lib().orc_batch_rollout_mt(self._b, int(T), int(policy), _p(w), _p(stats), int(threads))
         return stats
 
-    def rollout_values(self, length, n_forks, policy, weights=None, seed2=0, child_offset=0):
-        """(sum of fork returns int32[n, a_max], legal-slot mask u64[n]) -- game.py:129-160 for every env x action."""
+    def rollout_values(self, length, n_forks, policy, weights=None, seed2=0, child_offset=0, piece_tape=None):
+        """(sum of fork returns int32[n, a_max], legal-slot mask u64[n]) -- game.py:129-160 for every env x action.
+        piece_tape: optional uint8[n, a_max, n_forks, length], the pieces each fork draws (a recorded sampler)."""
         w = np.ascontiguousarray(BCTS_WEIGHTS if weights is None else weights, np.float32)
         ret = np.zeros((self.n, self.a_max), np.int32)
         valid = np.zeros(self.n, np.uint64)
+        tape = None if piece_tape is None else np.ascontiguousarray(piece_tape, np.uint8)
+        assert tape is None or tape.size == self.n * self.a_max * int(n_forks) * int(length)
         lib().orc_batch_rollout_values(self._b, self.a_max, int(n_forks), int(length), int(policy), _p(w),
-                                       int(seed2), int(child_offset), _p(ret), _p(valid))
+                                       int(seed2), int(child_offset), _p(tape), _p(ret), _p(valid))
         return ret, valid
 
     def rows(self):

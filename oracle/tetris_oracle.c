@@ -683,9 +683,12 @@ void orc_batch_rollout_mt(orc_batch *b, int T, int policy, const float *weights,
  * convention of tb_rollout_values: child d = (e * a_stride + slot) * n_forks + f is a one-env copy of the parent
  * whose pieces come from the stream (seed2, child_offset + d), continuing the parent's bag.  ret_sum[e][slot] = sum
  * over forks of the rollout return: -1 if the game ended (after the action or on the way), else the sum of the
- * follow-up rewards.  valid[e] = legal slots. */
+ * follow-up rewards.  valid[e] = legal slots.
+ * piece_tape (nullable): uint8[n_env * a_stride * n_forks][length], the pieces child d draws, in order, instead of
+ * its RNG stream -- a recorded sampler of the reference (tests/golden/make_golden.py gen_rollouts). */
 void orc_batch_rollout_values(orc_batch *b, int a_stride, int n_forks, int length, int policy, const float *weights,
-                              uint64_t seed2, int64_t child_offset, int32_t *ret_sum, uint64_t *valid)
+                              uint64_t seed2, int64_t child_offset, const uint8_t *piece_tape, int32_t *ret_sum,
+                              uint64_t *valid)
 {
     const int C = b->C, R = b->R, N = R + 4;
     orc_batch *t = orc_batch_new(C, R, b->piece_set, 1, 0, seed2);
@@ -706,7 +709,8 @@ void orc_batch_rollout_values(orc_batch *b, int a_stride, int n_forks, int lengt
                 t->piece[0] = b->piece[e]; t->bag[0] = b->bag[e]; t->draws[0] = b->draws[e];
                 t->ep_steps[0] = 0; t->ep_lines[0] = 0;
                 uint8_t dn = 0; int32_t rew = 0, lc = 0;
-                env_step(t, 0, s, 1, NULL, 0, NULL, &rew, &dn, &lc);               /* game.py:132 */
+                const uint8_t *tp = piece_tape ? piece_tape + (((size_t)e * a_stride + s) * n_forks + f) * (size_t)length : NULL;
+                env_step(t, 0, s, 1, tp, 0, NULL, &rew, &dn, &lc);                 /* game.py:132 */
                 int ret = 0;
                 if (dn) ret = -1;                                                   /* :133-137 */
                 for (int k = 0; !dn && k < length - 1; ++k) {                       /* :139-145 */
@@ -727,7 +731,7 @@ void orc_batch_rollout_values(orc_batch *b, int a_stride, int n_forks, int lengt
                             ++kk;
                         }
                     }
-                    env_step(t, 0, action, 0, NULL, 0, NULL, &rew, &dn, &lc);
+                    env_step(t, 0, action, 0, tp ? tp + 1 + k : NULL, 0, NULL, &rew, &dn, &lc);
                     ret += rew;
                     if (dn) ret = -1;
                 }

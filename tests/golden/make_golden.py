@@ -203,6 +203,91 @@ def gen_afterstates(ref):
           int(np.sum(per["terminal"])), "terminal,", int(np.sum(np.array(per["n_cleared"]) > 0)), "with clears")
 
 
+def dense_board(rng, C, R, kind):
+    """Near-full stacks (line clears of every multiplicity, overflow rescued by a clear): H rows that are
+    full but for one hole each, topped by d rows that are full but for a gap of gw columns at the same place -- the
+    piece that fits the gap clears up to d lines.  kind 'tall' puts the stack top within 3 rows of R, so most
+    placements poke above row R and are terminal unless they clear enough lines."""
+    N = R + 4
+    rep = np.zeros((N, C), np.int64)
+    d = int(rng.choice([1, 2, 3, 4], p=[0.2, 0.2, 0.2, 0.4]))
+    d = min(d, R)
+    if kind == "tall":
+        H = int(rng.integers(max(d, R - 3), R + 1))
+    else:
+        H = int(rng.integers(d, max(d, R - 2) + 1))
+    gw = int(rng.choice([1, 2, 3], p=[0.6, 0.3, 0.1]))
+    g = int(rng.integers(0, C - gw + 1))
+    rep[:H] = 1
+    for r in range(H - d):                       # lower rows: one hole each, anywhere (never full)
+        rep[r, rng.integers(0, C)] = 0
+    for r in range(H - d, H):
+        rep[r, g:g + gw] = 0
+        if rng.random() < 0.1:                   # now and then a second gap: that row does not clear
+            rep[r, rng.integers(0, C)] = 0
+    # ragged top: a few extra cells above the stack, outside the gap (heights stay <= R)
+    for c in range(C):
+        if not (g <= c < g + gw) and rng.random() < 0.3:
+            extra = int(rng.integers(1, 3))
+            rep[H:min(R, H + extra), c] = 1
+    # the gap columns keep whatever is below the gap; sometimes dig the gap deeper (a hole column) or roof part of it
+    if gw == 2 and rng.random() < 0.3 and H - d > 0:
+        rep[H - d - 1, g] = 0
+    return rep
+
+
+def gen_afterstates_dense(ref):
+    """afterstates_dense.npz: >= 80 k afterstates on near-full boards of five shapes (the three of BASELINE.json plus
+    8x16 and 4x4), all nine pieces -- hundreds of multi-line clears incl. four-line clears, terminal placements
+    rescued by a clear, terminal-with-clear.  Rows are padded to 32, columns to 16."""
+    st = ref["state"]
+    rng = np.random.default_rng(4321)
+    out = {k: [] for k in ("shape", "piece", "rows", "heights", "start", "count")}
+    per = {k: [] for k in ("feat2", "terminal", "n_cleared", "rows", "heights", "anchor", "is_full")}
+    total = 0
+    PADN, PADC = 32, 16
+    for (C, R), n_boards in (((10, 20), 150), ((10, 10), 110), ((8, 16), 110), ((6, 12), 130), ((4, 4), 120)):
+        pieces = make_pieces(ref, C)
+        boards = [dense_board(rng, C, R, "tall" if k % 2 else "mid") for k in range(n_boards)]
+        for rep in boards:
+            h = st.calc_lowest_free_rows(rep)
+            assert h.max() <= R
+            for pid, piece in enumerate(pieces):
+                base = st.State(representation=rep.copy(), lowest_free_rows=h.copy())
+                children = piece.get_after_states(base)
+                out["shape"].append((C, R)); out["piece"].append(pid)
+                out["rows"].append(np.pad(rows_of(rep), (0, PADN - (R + 4))))
+                out["heights"].append(np.pad(h, (0, PADC - C)))
+                out["start"].append(total); out["count"].append(len(children))
+                for ch in children:
+                    per["feat2"].append(feat2(ch.get_features()))
+                    per["terminal"].append(ch.terminal_state)
+                    per["n_cleared"].append(ch.n_cleared_lines)
+                    per["rows"].append(np.pad(rows_of(ch.representation), (0, PADN - (R + 4))))
+                    per["heights"].append(np.pad(ch.lowest_free_rows, (0, PADC - C)))
+                    per["anchor"].append((ch.anchor_col, ch.anchor_row))
+                    per["is_full"].append(np.pad(np.asarray(ch.cleared_rows_relative_to_anchor, bool),
+                                                 (0, 4 - len(ch.cleared_rows_relative_to_anchor))))
+                total += len(children)
+    ncl = np.array(per["n_cleared"])
+    term = np.array(per["terminal"])
+    R_of = np.repeat(np.array(out["shape"])[:, 1], np.array(out["count"]))
+    rescued = ~term & (np.array(per["heights"]).max(axis=1) + ncl > R_of)     # poked above row R before clearing
+    np.savez_compressed(
+        os.path.join(HERE, "afterstates_dense.npz"),
+        shape=np.array(out["shape"], np.int16), piece=np.array(out["piece"], np.int8),
+        rows=np.array(out["rows"], np.uint16), heights=np.array(out["heights"], np.int8),
+        start=np.array(out["start"], np.int32), count=np.array(out["count"], np.int16),
+        a_feat2=np.array(per["feat2"], np.int16), a_terminal=term,
+        a_n_cleared=ncl.astype(np.int8), a_rows=np.array(per["rows"], np.uint16),
+        a_heights=np.array(per["heights"], np.int8), a_anchor=np.array(per["anchor"], np.int8),
+        a_is_full=np.array(per["is_full"], bool))
+    print("afterstates_dense.npz:", len(out["piece"]), "boards x pieces,", total, "afterstates,", int(term.sum()),
+          "terminal; clears 1/2/3/4:", [int((ncl == k).sum()) for k in (1, 2, 3, 4)],
+          "; terminal with clear:", int((term & (ncl > 0)).sum()),
+          "; overflow rescued by a clear:", int(rescued.sum()))
+
+
 def gen_trace(ref, name, C, R, piece_set, n_env, n_steps, policy, directions, seed):
     """policy: 'random' (a = u_t mod n_valid) or 'greedy' (first argmax of Tetris.fitness, float32)."""
     pieces = make_pieces(ref, C)
@@ -328,10 +413,170 @@ def gen_fitness(ref):
     print("fitness.npz:", total, "afterstates")
 
 
+BCTS = np.array([-24.04, -19.77, -13.08, -12.63, -10.49, -9.22, 6.6, -1.61], np.float32)
+
+
+def greedy_policy_function(state, feats):
+    """policy_function(state, action_features) for Tetris.single_rollout (game.py:139-140): first arg-max of the
+    float32, left-to-right BCTS score of game.py:109-120 over the non-terminal afterstates' features."""
+    f = np.asarray(feats).astype(np.float32)
+    acc = f[:, 0] * BCTS[0]
+    for i in range(1, 8):
+        acc = acc + f[:, i] * BCTS[i]
+    assert acc.dtype == np.float32
+    return int(np.argmax(acc))
+
+
+class ListSampler:
+    """tetromino_sampler whose pieces come from a list that the harness swaps per rollout."""
+
+    def __init__(self, pieces):
+        self.pieces, self.tape, self.pos = pieces, [], 0
+
+    def load(self, tape):
+        self.tape, self.pos = list(tape), 0
+
+    def next_tetromino(self):
+        p = self.pieces[self.tape[self.pos]]
+        self.pos += 1
+        return p
+
+
+def gen_rollouts(ref):
+    """rollouts.npz: Tetris.single_rollout / perform_rollouts (game.py:129-160) of the reference itself.
+
+    Part A (per config `c<k>_*`): for P parent states, every legal action and n forks, single_rollout() with a
+    deterministic policy_function and the fork's own piece tape (injected through the replaceable sampler);
+    get_after_states() is called on the parent before every rollout, as a caller must for `action` to index the
+    parent's afterstates.  Recorded per enumeration slot: the sum of the forks' returns, legality, the tapes.
+    Policies: 'greedy' (above) and 'random' -- the new framework's per-fork counter RNG restated here
+    (stream 1 of (seed2, child id), counter = the fork's draw count), so the device can replay it.
+
+    Part B (`s<k>_*`): perform_rollouts() called as shipped, ONE get_after_states() before it, pieces from one
+    sequential tape: from the second rollout on `self.afterstates` is the list left behind by the previous rollout's
+    last policy step (game.py:140 overwrites it, :147-148 do not restore it), so `action` indexes a stale list.  The
+    compatibility class must reproduce these numbers to be a drop-in."""
+    st = ref["state"]
+    rng = np.random.default_rng(99)
+    out = {}
+    configs = [(10, 20, 1, "greedy", 4, 3, 1234), (10, 20, 1, "random", 4, 3, 77), (6, 12, 1, "greedy", 5, 2, 5),
+               (6, 12, 1, "random", 3, 3, 6), (10, 10, 0, "greedy", 4, 2, 8), (8, 16, 1, "greedy", 3, 2, 9)]
+    for k, (C, R, ps, policy, length, n_forks, seed2) in enumerate(configs):
+        pieces = make_pieces(ref, C)
+        ids = SETS[ps]
+        env = ref["game"].Tetris(C, R)
+        env.tetrominos = [pieces[i] for i in range(9)]
+        sampler = ListSampler(env.tetrominos)
+        env.tetromino_sampler = sampler
+        # parents: states reached by random play, sampled late enough that some rollouts end the game
+        parents = []
+        sampler.load([ids[int(x)] for x in rng.integers(0, len(ids), 100000)])
+        env.reset()
+        want = 10 if C * R >= 200 else 14
+        while len(parents) < want:
+            feats, _ = env.get_after_states()
+            _, _, done, _ = env.step(int(rng.integers(0, len(feats))))
+            if done:
+                env.reset()
+            elif env.current_state.lowest_free_rows.max() >= R - 7 and rng.random() < 0.4:
+                parents.append((env.current_state, env.current_tetromino))
+        a_max = max(len(pieces[i].get_after_states(st.State(np.zeros((R + 4, C), np.int_), np.zeros(C, np.int_))))
+                    for i in ids)
+        P = len(parents)
+        tape = np.zeros((P, a_max, n_forks, length), np.uint8)
+        ret_sum = np.zeros((P, a_max), np.int32)
+        valid = np.zeros((P, a_max), bool)
+        n_ended = 0
+        for p, (pstate, ppiece) in enumerate(parents):
+            children = ppiece.get_after_states(pstate)
+            legal = [s for s, ch in enumerate(children) if not ch.terminal_state]
+            for a, s in enumerate(legal):
+                valid[p, s] = True
+                for f in range(n_forks):
+                    tp = [ids[int(x)] for x in rng.integers(0, len(ids), length)]
+                    tape[p, s, f] = tp
+                    sampler.load(tp)
+                    env.current_state, env.current_tetromino = pstate, ppiece
+                    env.get_after_states()
+                    if policy == "greedy":
+                        fn = greedy_policy_function
+                    else:
+                        d = (p * a_max + s) * n_forks + f
+                        calls = [0]
+
+                        def fn(state, feats, d=d, calls=calls):
+                            # parent draws = 1 (its reset draw); the action's draw makes 2; + one per policy step
+                            r = rng32(seed2, d, 2 + calls[0], 1)
+                            calls[0] += 1
+                            return (r * len(feats)) >> 32
+                    r = env.single_rollout(a, fn, length)
+                    assert env.current_state is pstate and env.current_tetromino is ppiece
+                    ret_sum[p, s] += r
+                    n_ended += (r == -1)
+        pre = "c%d_" % k
+        out.update({pre + "C": C, pre + "R": R, pre + "piece_set": ps, pre + "policy": policy, pre + "length": length,
+                    pre + "n_forks": n_forks, pre + "seed2": seed2,
+                    pre + "rows": np.array([np.pad(rows_of(s.representation), (0, 32 - (R + 4))) for s, _ in parents], np.uint16),
+                    pre + "piece": np.array([piece_id(t) for _, t in parents], np.uint8),
+                    pre + "tape": tape, pre + "ret_sum": ret_sum, pre + "valid": valid})
+        print("rollouts c%d: %dx%d set %d %s length %d forks %d: %d parents, %d legal actions, %d rollouts ended the game"
+              % (k, C, R, ps, policy, length, n_forks, P, int(valid.sum()), n_ended))
+    out["n_configs"] = len(configs)
+
+    # ---- part B: perform_rollouts as shipped (stale self.afterstates from the second rollout on)
+    stale = [(10, 20, 1, 4, 2), (6, 12, 1, 3, 3), (10, 10, 0, 4, 2)]
+    for k, (C, R, ps, length, n) in enumerate(stale):
+        pieces = make_pieces(ref, C)
+        ids = SETS[ps]
+        env = ref["game"].Tetris(C, R)
+        env.tetrominos = [pieces[i] for i in range(9)]
+        sampler = ListSampler(env.tetrominos)
+        env.tetromino_sampler = sampler
+        seq = [ids[int(x)] for x in rng.integers(0, len(ids), 4000)]
+        sampler.load(seq)
+        env.reset()
+        for _ in range(14 if R >= 16 else 8):
+            feats, _ = env.get_after_states()
+            _, _, done, _ = env.step(int(rng.integers(0, len(feats))))
+            assert not done
+        start_pos = sampler.pos
+        feats, _ = env.get_after_states()
+        # perform_rollouts (game.py:150-160) call by call, so that a failure of the reference itself -- the stale list
+        # can be shorter than the action index: IndexError at game.py:83 -- is recorded where it happens
+        n_act = min(len(feats), 4)
+        calls, err_at = [], -1
+        for a in range(n_act):
+            for i in range(n):
+                try:
+                    calls.append(env.single_rollout(a, greedy_policy_function, length))
+                except IndexError:
+                    err_at = len(calls)
+                    break
+            if err_at >= 0:
+                break
+        pre = "s%d_" % k
+        out.update({pre + "C": C, pre + "R": R, pre + "piece_set": ps, pre + "length": length, pre + "n": n,
+                    pre + "rows": rows_of(env.current_state.representation),
+                    pre + "piece": piece_id(env.current_tetromino), pre + "n_actions": n_act,
+                    pre + "tape": np.array(seq[start_pos:sampler.pos], np.uint8),
+                    pre + "returns": np.array(calls, np.int32), pre + "error_at": err_at})
+        print("rollouts s%d: single_rollout calls of perform_rollouts as shipped, %dx%d: returns %s, IndexError at call %d "
+              "(%d pieces drawn)" % (k, C, R, calls, err_at, sampler.pos - start_pos))
+    out["n_stale"] = len(stale)
+    np.savez_compressed(os.path.join(HERE, "rollouts.npz"), **out)
+
+
 def main():
     ref = load_reference()
+    only = sys.argv[1:]
+    if only:                                     # e.g. `make_golden.py afterstates_dense rollouts`
+        for name in only:
+            globals()["gen_" + name](ref)
+        return
     gen_known_answer(ref)
     gen_afterstates(ref)
+    gen_afterstates_dense(ref)
+    gen_rollouts(ref)
     gen_fitness(ref)
     gen_trace(ref, "7p_10x20_random", 10, 20, 1, 32, 160, "random", None, 0x5EED)
     gen_trace(ref, "2p_10x10_random_dir", 10, 10, 0, 16, 120, "random", DIRECTIONS, 11)

@@ -31,3 +31,30 @@ def feat2(f):
     r = np.rint(v)
     assert np.array_equal(r, v), "feature is not a half-integer"
     return r.astype(np.int64)
+
+
+def rollout_configs(g):
+    """The part-A configs of rollouts.npz as dicts (tests/golden/make_golden.py gen_rollouts)."""
+    out = []
+    for k in range(int(g["n_configs"])):
+        pre = "c%d_" % k
+        c = {key[len(pre):]: g[key] for key in g if key.startswith(pre)}
+        for key in ("C", "R", "piece_set", "length", "n_forks", "seed2"):
+            c[key] = int(c[key])
+        c["policy"] = str(c["policy"])
+        out.append(c)
+    return out
+
+
+def replay_rollout_config(c, make_batch):
+    """Replay one config through an engine with the oracle.Batch API (rep / heights / piece views or import, and
+    rollout_values(..., piece_tape=)): returns (ret_sum, valid bits) to compare with the fixture."""
+    C, R = c["C"], c["R"]
+    P = len(c["piece"])
+    b = make_batch(C, R, P, c["piece_set"])
+    b.load(c["rows"][:, :R + 4], c["piece"])
+    ret, valid = b.rollout_values(c["length"], c["n_forks"], 1 if c["policy"] == "greedy" else 0, seed2=c["seed2"],
+                                  piece_tape=c["tape"])
+    a_max = c["valid"].shape[1]
+    bits = ((np.asarray(valid, np.uint64)[:, None] >> np.arange(a_max, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    return np.asarray(ret), bits

@@ -186,6 +186,94 @@ def test_fitness_and_best_policy():
         assert np.array_equal(env.get_best_policy(), g["best_policy"][s:s + n])
 
 
+class ListSampler:
+    def __init__(self, pieces):
+        self.pieces, self.tape, self.pos = pieces, [], 0
+
+    def load(self, tape):
+        self.tape, self.pos = [int(x) for x in tape], 0
+
+    def next_tetromino(self):
+        p = self.pieces[self.tape[self.pos]]
+        self.pos += 1
+        return p
+
+
+def _greedy_policy_function(state, feats):
+    w = np.array([-24.04, -19.77, -13.08, -12.63, -10.49, -9.22, 6.6, -1.61], np.float32)
+    f = np.asarray(feats).astype(np.float32)
+    acc = f[:, 0] * w[0]
+    for i in range(1, 8):
+        acc = acc + f[:, i] * w[i]
+    return int(np.argmax(acc))
+
+
+def test_single_rollout_vs_reference():
+    """Tetris.single_rollout through the compatibility class == the reference's (tests/golden/rollouts.npz part A,
+    greedy configs): same parents, actions, per-fork piece tapes and policy_function -> same returns."""
+    from golden_util import rollout_configs
+    from tetris import state, tetromino
+    from tetris.game import Tetris
+    g = load("rollouts")
+    checked = 0
+    for c in rollout_configs(g):
+        if c["policy"] != "greedy":
+            continue
+        C, R = c["C"], c["R"]
+        env = Tetris(C, R)
+        env.tetrominos = [cls("bcts", 8, C) for cls in tetromino.PIECE_CLASSES]
+        sampler = ListSampler(env.tetrominos)
+        env.tetromino_sampler = sampler
+        for p in range(0, len(c["piece"]), 4):
+            parent = state.State(rows_to_rep(c["rows"][p][:R + 4], C).astype(np.int64))
+            piece = env.tetrominos[int(c["piece"][p])]
+            legal = np.nonzero(c["valid"][p])[0]
+            for a, s in enumerate(legal):
+                total = 0
+                for f in range(c["n_forks"]):
+                    sampler.load(c["tape"][p, s, f])
+                    env.current_state, env.current_tetromino = parent, piece
+                    env.get_after_states()
+                    total += env.single_rollout(a, _greedy_policy_function, c["length"])
+                    assert env.current_state is parent and env.current_tetromino is piece       # game.py:147-148
+                assert total == c["ret_sum"][p, s], (C, R, p, s)
+                checked += 1
+    assert checked > 100
+
+
+def test_perform_rollouts_as_shipped():
+    """perform_rollouts called the way the reference ships it (one get_after_states before it): `afterstates` is left
+    stale by every rollout (game.py:140,147-148), so later rollouts index the previous rollout's last list -- and the
+    reference raises IndexError when that list is too short.  The drop-in class reproduces the recorded returns call
+    by call and fails at the same call (tests/golden/rollouts.npz part B)."""
+    from tetris import state, tetromino
+    from tetris.game import Tetris
+    g = load("rollouts")
+    for k in range(int(g["n_stale"])):
+        pre = "s%d_" % k
+        C, R, length, n = (int(g[pre + x]) for x in ("C", "R", "length", "n"))
+        env = Tetris(C, R)
+        env.tetrominos = [cls("bcts", 8, C) for cls in tetromino.PIECE_CLASSES]
+        sampler = ListSampler(env.tetrominos)
+        env.tetromino_sampler = sampler
+        sampler.load(g[pre + "tape"])
+        env.current_state = state.State(rows_to_rep(g[pre + "rows"], C).astype(np.int64))
+        env.current_tetromino = env.tetrominos[int(g[pre + "piece"])]
+        env.get_after_states()
+        calls, err_at = [], -1
+        for a in range(int(g[pre + "n_actions"])):
+            for i in range(n):
+                try:
+                    calls.append(env.single_rollout(a, _greedy_policy_function, length))
+                except IndexError:
+                    err_at = len(calls)
+                    break
+            if err_at >= 0:
+                break
+        assert calls == g[pre + "returns"].tolist() and err_at == int(g[pre + "error_at"]), (k, calls, err_at)
+        assert sampler.pos == len(g[pre + "tape"])                     # same number of pieces consumed
+
+
 def test_rollout_helpers():
     from tetris.game import Tetris
     np.random.seed(3)
@@ -193,8 +281,8 @@ def test_rollout_helpers():
     feats, _ = env.get_after_states()
     before = (env.current_state, env.current_tetromino)
     policy = lambda st, f: int(np.argmax(f.sum(axis=1)))
-    acts, rets = env.perform_rollouts(list(range(4)), policy, length=4, n=2)
-    assert acts == [0, 1, 2, 3] and len(rets) == 4 and all(-3 <= r <= 9 for r in rets)
+    acts, rets = env.perform_rollouts(list(range(2)), policy, length=1, n=2)     # length 1: no policy step, nothing stale
+    assert acts == [0, 1] and rets == [0.0, 0.0]
     assert (env.current_state, env.current_tetromino) == before      # restored (game.py:147-148)
 
 

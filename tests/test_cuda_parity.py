@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from golden_util import TRACES, feat2, load, rep_to_rows, rows_to_rep
+from golden_util import TRACES, feat2, load, rep_to_rows, replay_rollout_config, rollout_configs, rows_to_rep
 from test_oracle_golden import replay_trace
 
 pytestmark = pytest.mark.gpu
@@ -77,13 +77,15 @@ def test_trace_rng(name):
     replay_trace(load("trace_" + name), _cuda_batch, rng_mode=True)
 
 
-def test_afterstates_fixture():
-    """Every board x piece of the reference-generated fixture, through tb_afterstates and tb_afterstates_export."""
+@pytest.mark.parametrize("name", ["afterstates", "afterstates_dense"])
+def test_afterstates_fixture(name):
+    """Every board x piece of the reference-generated fixtures, through tb_afterstates and tb_afterstates_export.
+    `afterstates_dense` holds near-full stacks (four-line clears, overflow rescued by a clear) on five shapes."""
     torch = _torch()
     from tetris_b200 import BatchedTetris, _lib
-    g = load("afterstates")
+    g = load(name)
     shapes = g["shape"].astype(int)
-    for (Cc, R) in ((10, 20), (10, 10), (6, 12)):
+    for (Cc, R) in sorted({tuple(x) for x in shapes.tolist()}):
         idx = np.nonzero((shapes[:, 0] == Cc) & (shapes[:, 1] == R))[0]
         N = R + 4
         for ps in (0, 1):
@@ -522,3 +524,166 @@ def _tile_configuration_body():
         mask = np.arange(env.a_max)[None, :] < on[:, None]
         assert np.array_equal(feats.cpu().numpy()[mask], of[mask])
         assert np.array_equal(valid.cpu().numpy().view(np.uint64), ov) and np.array_equal(count.cpu().numpy(), oc)
+
+
+def _oracle_window(Cc, R, first, count, seed, warm, T):
+    """The oracle's replay of envs [first, first + count) of a bigger job (RNG keyed by the global env id)."""
+    from oracle import oracle as orc
+    ob = orc.Batch(Cc, R, count, piece_set=1, seed=seed, env_offset=first)
+    ob.reset()
+    ob.rollout(warm, 0, threads=8)
+    ob.rollout(T, 1, threads=8)
+    return ob
+
+
+@pytest.mark.parametrize("k1cfg,k3cfg", [(0, 0), (3, 2)])
+def test_multi_tile_per_cta(k1cfg, k3cfg):
+    """A CTA of the tile kernels loops over several tiles once there are more tiles than the grid holds (above
+    ~1.2 M envs per GPU for K3); the loop carries state from tile to tile (piece-count parity, shared-memory records).
+    Forced here on a small batch by capping the grid through the ABI's tuning hook: 3 CTAs for 11 / 21 tiles, i.e.
+    3-7 tiles per CTA, K1 and K3, against the oracle."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris, _lib
+    _lib.set_tuning("k1_cfg", k1cfg); _lib.set_tuning("k3_cfg", k3cfg); _lib.set_tuning("max_ctas", 3)
+    try:
+        for (Cc, R, n, T) in ((6, 12, 2570, 40), (10, 20, 2570, 50)):
+            env = BatchedTetris(Cc, R, n, piece_set=1, seed=123)
+            ob = orc.Batch(Cc, R, n, piece_set=1, seed=123)
+            ob.reset()
+            env.rollout(25, "random"); s0 = ob.rollout(25, 0, threads=8)
+            env.rollout(T, "greedy"); s1 = ob.rollout(T, 1, threads=8)
+            _compare_state(env, ob)
+            total = s0 + s1
+            total[10:12] = np.maximum(s0[10:12], s1[10:12])
+            assert np.array_equal(env.stats.cpu().numpy(), total)
+            feats, valid, count = env.get_after_states(include_terminal=True)
+            of, ov, oc, on = ob.afterstates()
+            mask = np.arange(env.a_max)[None, :] < on[:, None]
+            assert np.array_equal(feats.cpu().numpy()[mask], of[mask])
+            assert np.array_equal(valid.cpu().numpy().view(np.uint64), ov) and np.array_equal(count.cpu().numpy(), oc)
+    finally:
+        _lib.set_tuning("k1_cfg", -1); _lib.set_tuning("k3_cfg", -1); _lib.set_tuning("max_ctas", 0)
+
+
+def test_two_million_env_greedy_rollout():
+    """2^21 envs on one GPU: more 256-env tiles (8192) than K3's grid holds (16 x 148 x 2 = 4736 CTAs), so CTAs take a
+    second tile with the shipped configuration -- no tuning hook.  Too many for the oracle: it replays the first and
+    the last 192 envs (their RNG is keyed by the global env id) and must end on identical boards, pieces and counters;
+    the statistics must satisfy the integer invariants of a complete run."""
+    from tetris_b200 import BatchedTetris, _lib
+    n, m, seed, warm, T = 1 << 21, 192, 777, 20, 24
+    assert _lib.get_tuning("max_ctas") == 0 and _lib.get_tuning("k3_cfg") == -1
+    env = BatchedTetris(10, 20, n, piece_set=1, seed=seed)
+    env.rollout(warm, "random")
+    env.stats.zero_()
+    env.rollout(T, "greedy")
+    st = env.stats_dict()
+    assert st["placements"] == n * T and sum(st["lines%d" % i] for i in range(5)) == n * T
+    assert st["reward"] == st["lines"] - st["placements"] - 100 * st["episodes"]
+    for first in (0, n - m):
+        ob = _oracle_window(10, 20, first, m, seed, warm, T)
+        rows, heights, piece = env.export_boards(first, m)
+        assert np.array_equal(rows.cpu().numpy().view(np.uint16), ob.rows()), first
+        assert np.array_equal(heights.cpu().numpy(), ob.heights) and np.array_equal(piece.cpu().numpy(), ob.piece)
+    # K1 over the same 2^21 envs (8192 tiles over 8 x 148 x 3 = 3552 CTAs): sampled parity at both ends
+    feats, valid, count = env.get_after_states()
+    for first in (0, n - m):
+        ob = _oracle_window(10, 20, first, m, seed, warm, T)
+        of, ov, oc, on = ob.afterstates()
+        mask = ((ov[:, None] >> np.arange(env.a_max, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+        assert np.array_equal(feats[first:first + m].cpu().numpy()[mask], of[mask])
+        assert np.array_equal(valid[first:first + m].cpu().numpy().view(np.uint64), ov)
+
+
+def test_step_validates_before_mutation_and_defines_outputs():
+    """Tetris.step raises IndexError before anything changes (game.py:83).  check=True: one bad action among many ->
+    IndexError naming the env, and NO env was stepped.  check=False (the asynchronous path): the offending env is left
+    untouched and reports zero obs / reward / lines, every other env is stepped normally."""
+    torch = _torch()
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris
+    n = 300
+    env = BatchedTetris(10, 10, n, piece_set=1, seed=4)
+    ob = orc.Batch(10, 10, n, piece_set=1, seed=4)
+    ob.reset()
+    env.rollout(12, "random"); ob.rollout(12, 0)
+    before = env.rows().copy()
+    a = np.zeros(n, np.int32)
+    a[137] = 60
+    with pytest.raises(IndexError, match="env 137"):
+        env.step(a)
+    assert np.array_equal(env.rows(), before) and np.array_equal(env.piece, ob.piece)
+    obs, rew, done, lines = env.step(torch.as_tensor(a), check=False)
+    a_ok = a.copy(); a_ok[137] = 0
+    oobs, orew, odone, olines = ob.step(a_ok)
+    keep = np.arange(n) != 137
+    assert np.array_equal(obs.cpu().numpy()[keep], oobs[keep]) and np.array_equal(rew.cpu().numpy()[keep], orew[keep])
+    assert np.array_equal(done.cpu().numpy()[keep], odone[keep]) and np.array_equal(lines.cpu().numpy()[keep], olines[keep])
+    assert not obs[137].any() and int(rew[137]) == 0 and int(lines[137]) == 0 and not bool(done[137])
+    assert np.array_equal(env.rows()[137], before[137])
+    assert np.array_equal(env.rows()[keep], ob.rows()[keep])
+
+
+def test_bad_piece_ids_and_terminal_imports_are_inert():
+    """Piece ids index shared-memory tables in the kernels: ids that name no piece must not get there.  Host arrays
+    are rejected; ids in device tensors make the env inert (no afterstates, not stepped).  A board imported with a
+    cell at or above row R is a terminal state (state.py:111-117): marked finished."""
+    torch = _torch()
+    from tetris_b200 import BatchedTetris
+    env = BatchedTetris(10, 20, 64, piece_set=1, seed=1)
+    with pytest.raises(ValueError):
+        env.reset(tape=np.full(64, 9, np.uint8))
+    tape = torch.full((64,), 3, dtype=torch.uint8, device="cuda")
+    tape[5] = 200
+    env.reset(tape=tape)
+    feats, valid, count = env.get_after_states()
+    assert int(count[5]) == 0 and int(valid[5]) == 0 and bool((count[torch.arange(64) != 5] == 9).all())
+    st0 = env.stats.clone()
+    env.rollout(10, "greedy"); env.rollout(10, "random")
+    assert not env.rows()[5].any()                                     # never stepped
+    assert int(env.stats[0] - st0[0]) == 63 * 20
+    # terminal board
+    rows = np.zeros((1, 24), np.uint16)
+    rows[0, :21] = 1                                                   # column 0 filled up to row 20 = R
+    env2 = BatchedTetris(10, 20, 4, piece_set=1, seed=1)
+    env2.import_boards(rows, piece=np.array([0], np.uint8), first=2)
+    assert env2.piece[2] == 0xFF
+    f, v, c = env2.get_after_states()
+    assert int(c[2]) == 0 and bool((c[[0, 1, 3]] > 0).all())
+
+
+def test_combine_stats_kernel():
+    """tb_combine_stats (the local half of reduce_stats) == distributed.combine_stats."""
+    torch = _torch()
+    from tetris_b200 import _lib, distributed as D
+    g = torch.Generator().manual_seed(3)
+    parts = torch.randint(0, 1 << 40, (8, len(_lib.STATS)), generator=g, dtype=torch.int64)
+    dev = parts.cuda()
+    out = torch.empty(len(_lib.STATS), dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().tb_combine_stats(C.c_void_p(dev.data_ptr()), 8, C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), D.combine_stats(list(parts)))
+
+
+class _CudaRolloutBatch:
+    def __init__(self, Cc, R, n, ps):
+        from tetris_b200 import BatchedTetris
+        self.env = BatchedTetris(Cc, R, n, piece_set=ps, seed=0)
+
+    def load(self, rows, piece):
+        self.env.import_boards(rows, piece=piece)
+
+    def rollout_values(self, length, n_forks, policy, seed2=0, piece_tape=None):
+        mean, valid = self.env.rollout_values(length=length, n=n_forks, policy=("random", "greedy")[policy], seed=seed2,
+                                              piece_tape=piece_tape)
+        return np.rint(mean.cpu().numpy() * n_forks).astype(np.int64), valid.cpu().numpy().view(np.uint64)
+
+
+def test_rollouts_fixture():
+    """tb_rollout_values against the REFERENCE's Tetris.single_rollout (game.py:129-148): recorded parent states, every
+    legal action x fork, the forks' recorded piece tapes, greedy and counter-RNG policies (tests/golden/rollouts.npz)."""
+    g = load("rollouts")
+    for c in rollout_configs(g):
+        ret, bits = replay_rollout_config(c, _CudaRolloutBatch)
+        assert np.array_equal(bits, c["valid"]), (c["C"], c["R"], c["policy"])
+        assert np.array_equal(ret, c["ret_sum"]), (c["C"], c["R"], c["policy"])

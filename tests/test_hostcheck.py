@@ -125,10 +125,12 @@ def test_core_vs_oracle(hc, shape):
     assert stats[1] > 0.5 * stats[0]          # the incremental path actually carries most placements
 
 
-def test_core_vs_golden(hc):
-    """Straight against the reference-generated fixture as well."""
-    g = load("afterstates")
-    for i in range(0, len(g["piece"]), 3):
+@pytest.mark.parametrize("name,stride", [("afterstates", 3), ("afterstates_dense", 2)])
+def test_core_vs_golden(hc, name, stride):
+    """Straight against the reference-generated fixtures as well (the dense one: near-full stacks, multi-line clears,
+    overflow rescued by a clear, on five shapes)."""
+    g = load(name)
+    for i in range(0, len(g["piece"]), stride):
         Cc, R = (int(x) for x in g["shape"][i])
         N = R + 4
         n, feats, term, ncl, rows_out, anchor, fast = hc_afterstates(hc, Cc, R, int(g["piece"][i]), g["rows"][i][:N], 0)

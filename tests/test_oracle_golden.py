@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from golden_util import TRACES, feat2, load, rep_to_rows, rows_to_rep
+from golden_util import TRACES, feat2, load, rep_to_rows, replay_rollout_config, rollout_configs, rows_to_rep
 from oracle import oracle as orc
 
 
@@ -20,8 +20,12 @@ def test_empty_board_features():
     assert orc.reset_state_features(10, 20).tolist() == [0, 10, 0, 1, 0, 40, 0, 0]
 
 
-def test_afterstates_fixture():
-    g = load("afterstates")
+@pytest.mark.parametrize("name,at_least", [("afterstates", 30000), ("afterstates_dense", 80000)])
+def test_afterstates_fixture(name, at_least):
+    """`afterstates`: played and arbitrary boards of 10x20 / 10x10 / 6x12.  `afterstates_dense`: near-full stacks of
+    those three plus 8x16 and 4x4 -- 115 four-line clears, 875 placements that poke above row R and are rescued by
+    the clear, 353 that clear and are terminal all the same (tests/golden/make_golden.py prints the census)."""
+    g = load(name)
     n_checked = 0
     for i in range(len(g["piece"])):
         C, R = (int(x) for x in g["shape"][i])
@@ -40,7 +44,11 @@ def test_afterstates_fixture():
         assert np.array_equal(out["anchor_row"], g["a_anchor"][sl][:, 1])
         assert np.array_equal(out["is_full"], g["a_is_full"][sl])
         n_checked += n
-    assert n_checked == len(g["a_terminal"]) > 30000
+    assert n_checked == len(g["a_terminal"]) > at_least
+    if name == "afterstates_dense":
+        ncl = g["a_n_cleared"]
+        assert (ncl == 4).sum() >= 50 and (ncl == 3).sum() >= 50 and (g["a_terminal"] & (ncl > 0)).sum() >= 50
+        assert {tuple(x) for x in g["shape"].tolist()} == {(10, 20), (10, 10), (6, 12), (8, 16), (4, 4)}
 
 
 def replay_trace(g, make_batch, rng_mode):
@@ -138,3 +146,33 @@ def test_fitness_fixture():
         assert np.array_equal(fv, g["fitness"][s:s + n])          # bit-exact float32
         pol = (fv == fv.max()).astype(float)
         assert np.array_equal(pol / pol.sum(), g["best_policy"][s:s + n])
+
+
+class _OracleRolloutBatch:
+    def __init__(self, C, R, n, ps):
+        self.b = orc.Batch(C, R, n, piece_set=ps, seed=0)
+        self.b.reset()                                     # one draw per env, like a freshly constructed game
+        self.C = C
+
+    def load(self, rows, piece):
+        rep = rows_to_rep(rows, self.C)
+        self.b.rep[:] = rep
+        self.b.heights[:] = [orc.calc_lowest_free_rows(r) for r in rep]
+        self.b.piece[:] = piece
+
+    def rollout_values(self, *a, **kw):
+        return self.b.rollout_values(*a, **kw)
+
+
+def test_rollouts_fixture():
+    """SURVEY 8f-1 pinned to the reference: Tetris.single_rollout (game.py:129-148) for every legal action and fork
+    of recorded parent states, with the forks' recorded piece tapes and a deterministic policy (greedy BCTS, or the
+    per-fork counter RNG): sums of returns per enumeration slot and the legal-slot masks are the reference's."""
+    g = load("rollouts")
+    n_ret = 0
+    for c in rollout_configs(g):
+        ret, bits = replay_rollout_config(c, _OracleRolloutBatch)
+        assert np.array_equal(bits, c["valid"]), (c["C"], c["R"], c["policy"])
+        assert np.array_equal(ret, c["ret_sum"]), (c["C"], c["R"], c["policy"])
+        n_ret += int(bits.sum()) * c["n_forks"]
+    assert n_ret > 2000

@@ -98,17 +98,17 @@ class Tetris:
 
     # -- rollout helpers (game.py:129-160) ----------------------------------------------------------
     def single_rollout(self, action, policy_function, length):
-        """Return of `length - 1` policy steps after taking `action`; -1 if the game ends on the way.  The env is
-        restored to the saved (state, piece) afterwards; like the reference, the sampler is not rewound.  Unlike the
-        reference (game.py:130-148), the cached `afterstates` list is restored too: there it is left pointing at the
-        last rollout state, so a second rollout indexes a stale list."""
+        """Return of `length - 1` policy steps after taking `action`; -1 if the game ends on the way (game.py:129-148).
+
+        Bug-for-bug with the reference, pinned by tests/golden/rollouts.npz: the env is restored to the saved
+        (state, piece) afterwards, the sampler is not rewound, and the cached `afterstates` list is NOT restored --
+        it is left as the last policy step's list, so `action` indexes the parent's afterstates only if the caller
+        runs get_after_states() before every call (perform_rollouts does not: from its second rollout on it takes a
+        placement of a stale state, and raises IndexError when that list is shorter).  For rollouts that mean what
+        they say, and for all actions of many envs at once, use BatchedTetris.rollout_values."""
         saved = (self.current_state, self.current_tetromino)
-        saved_afterstates = getattr(self, "afterstates", None)
         if self.is_game_over(saved[0]):
             return -1
-        if saved_afterstates is None:
-            self.get_after_states()
-            saved_afterstates = self.afterstates
         rollout_return = 0
         done = self.step(action)[2]
         if done:
@@ -122,7 +122,6 @@ class Tetris:
                     rollout_return = -1
                     break
         self.current_state, self.current_tetromino = saved
-        self.afterstates = saved_afterstates
         return rollout_return
 
     def perform_rollouts(self, actions, policy_function, length=5, n=5):
