@@ -2,7 +2,7 @@
 # One GPU visit: parity tests, the bench line + reference arm, the ncu launch lists, and full captures of K1 / K3 / K2 /
 # the random rollout summarised ON the box (the four reports together exceed gpurun's 64 MiB return limit; only K1's
 # report travels back).  Usage (from the repo root, under gpurun):  bash profiles/gpu_round.sh [tag]
-tag=${1:-r1}
+tag=${1:-r2}
 out=gpurun_out; mkdir -p $out
 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 $out/pytest_gpu_$tag.log
 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?"; cut -c1-300 $out/bench_$tag.json

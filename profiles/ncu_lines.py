@@ -4,8 +4,10 @@
     python profiles/ncu_lines.py <report.ncu-rep> <kernel mangled-name substring> [top_n]
 
 Joins `ncu --page source --csv` (per SASS instruction: executed warp instructions, thread instructions,
-stall samples) with `nvdisasm --print-line-info-inline` of the cubin in csrc/libtetris_b200.so (built with
--lineinfo), by instruction offset.  Prints totals per innermost source line and per inlined callee.
+stall samples, shared-memory wavefronts) with `nvdisasm --print-line-info-inline` of the cubins in
+csrc/libtetris_b200.so (built with -lineinfo; TB_SO_PATH overrides the library), by instruction offset.  Prints
+totals per innermost source line, per kernel-body line and per opcode, and the shared-memory bank-conflict table:
+wavefronts, ideal wavefronts and excessive (= conflict replay) wavefronts per source line.
 """
 import collections
 import csv
@@ -16,50 +18,17 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO = os.path.join(ROOT, "tetris_b200", "csrc", "libtetris_b200.so")
-
-
-def disasm(kernel_sub):
-    tmp = tempfile.mkdtemp()
-    subprocess.check_call(["cuobjdump", "-xelf", "all", SO], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "--print-line-info-inline", "-c", os.path.join(tmp, cubin)],
-                         capture_output=True, text=True).stdout.splitlines()
-    out, cur, active = {}, [], False
-    for ln in txt:
-        if ln.startswith(".text.") and ln.endswith(":"):
-            active = kernel_sub in ln
-            cur = []
-            continue
-        if not active:
-            continue
-        m = re.match(r'\s*//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
-        if m:
-            cur.append((os.path.basename(m.group(1)), int(m.group(2))))
-            continue
-        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
-        if m:
-            off = int(m.group(1), 16)
-            # `cur` = chain innermost ... outermost for this instruction group; it persists until the next //## block
-            out[off] = list(cur)
-            pending = True
-        elif ln.strip().startswith(".L_") or not ln.strip():
-            pass
-        # a new //## group after an instruction starts a fresh chain
-        if m is None:
-            continue
-        cur_after = cur
-        cur = cur_after
-    return out
+SO = os.environ.get("TB_SO_PATH") or os.path.join(ROOT, "tetris_b200", "csrc", "libtetris_b200.so")
 
 
 def disasm_chains(kernel_sub):
     """offset -> [(file, line) innermost .. outermost]"""
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", SO], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "--print-line-info-inline", "-c", os.path.join(tmp, cubin)],
-                         capture_output=True, text=True).stdout.splitlines()
+    txt = []                                   # one cubin per translation unit (board shape): scan them all
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        txt += subprocess.run(["nvdisasm", "--print-line-info-inline", "-c", os.path.join(tmp, cubin)],
+                              capture_output=True, text=True).stdout.splitlines()
     out, chain, fresh, active = {}, [], True, False
     for ln in txt:
         if ln.startswith(".text.") and ln.endswith(":"):
@@ -94,7 +63,16 @@ def main():
     by_line = collections.defaultdict(lambda: [0, 0, 0])
     by_outer = collections.defaultdict(lambda: [0, 0, 0])
     by_op = collections.defaultdict(lambda: [0, 0, 0])
+    shm = collections.defaultdict(lambda: [0, 0, 0, 0])          # wavefronts, ideal, excessive, instructions
+    shm_tot = [0, 0, 0]
     tot = [0, 0, 0]
+
+    def num(r, name):
+        i = col.get(name)
+        try:
+            return int(float(r[i])) if i is not None and r[i] not in ("", "-") else 0
+        except ValueError:
+            return 0
     for r in rows[hdr_i + 1:]:
         if len(r) < len(hdr) or not r[0].startswith("0x"):
             continue
@@ -113,6 +91,11 @@ def main():
         op = op.split(".")[0]
         by_op[op][0] += inst; by_op[op][1] += thr; by_op[op][2] += smp
         tot[0] += inst; tot[1] += thr; tot[2] += smp
+        wf, ideal, exc = num(r, "L1 Wavefronts Shared"), num(r, "L1 Wavefronts Shared Ideal"), num(r, "L1 Wavefronts Shared Excessive")
+        if wf:
+            key = (inner, outer, op)
+            shm[key][0] += wf; shm[key][1] += ideal; shm[key][2] += exc; shm[key][3] += inst
+            shm_tot[0] += wf; shm_tot[1] += ideal; shm_tot[2] += exc
     print("total warp-inst %d  thread-inst %d  samples %d  (avg active threads %.1f)" % (tot[0], tot[1], tot[2], tot[1] / max(tot[0], 1)))
     for title, d in (("innermost source line", by_line), ("outermost (kernel-body) line", by_outer), ("opcode", by_op)):
         print("\n== by %s: warp-inst%%  thread-inst%%  samples%%  avg-threads" % title)
@@ -120,6 +103,16 @@ def main():
             name = "%s:%d" % k if isinstance(k, tuple) else k
             print("%-28s %6.2f %6.2f %6.2f  %5.1f" % (name, 100.0 * v[0] / tot[0], 100.0 * v[1] / max(tot[1], 1),
                                                      100.0 * v[2] / max(tot[2], 1), v[1] / max(v[0], 1)))
+    print_shared(shm, shm_tot, top)
+
+
+def print_shared(shm, shm_tot, top):
+    print("\n== shared memory: %d wavefronts, %d ideal, %d excessive (bank-conflict replays) = %.1f %% of wavefronts"
+          % (shm_tot[0], shm_tot[1], shm_tot[2], 100.0 * shm_tot[2] / max(shm_tot[0], 1)))
+    print("   innermost line <- kernel-body line, opcode: excessive%%-of-all-excessive  wavefronts  ideal  excessive  wavefronts/inst")
+    for (inner, outer, op), v in sorted(shm.items(), key=lambda kv: -kv[1][2])[:top]:
+        print("%-22s <- %-22s %-5s %6.2f %11d %11d %11d  %5.2f" % ("%s:%d" % inner, "%s:%d" % outer, op,
+              100.0 * v[2] / max(shm_tot[2], 1), v[0], v[1], v[2], v[0] / max(v[3], 1)))
 
 
 if __name__ == "__main__":
