@@ -1,0 +1,72 @@
+"""A/B of tile configurations on one GPU: K1 (tb_afterstates) and K3 (tb_rollout greedy) device times at 2^20 envs on
+greedy-play boards, per configuration (tb_set_tuning), L2 flushed between launches.
+
+    python profiles/ab_cfg.py [--k1 0,6,2] [--k3 0,6] [--envs N]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from tetris_b200 import BatchedTetris, _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--k1", default="0,6,2")
+ap.add_argument("--k3", default="0,6")
+ap.add_argument("--envs", type=int, default=1 << 20)
+ap.add_argument("--board", default="10x20")
+a = ap.parse_args()
+C, R = (int(x) for x in a.board.split("x"))
+n = a.envs
+env = BatchedTetris(C, R, n, piece_set=1, seed=0x5EED)
+env.rollout(30, "random")
+env.rollout(64, "greedy")
+saved = env.state.clone()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+feats = torch.empty((n, env.a_max, 8), dtype=torch.float32, device="cuda")
+valid = torch.empty(n, dtype=torch.int64, device="cuda")
+count = torch.empty(n, dtype=torch.int32, device="cuda")
+out = {"envs": n, "board": a.board}
+
+
+def timed(fn, reps):
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+for cfg in [int(x) for x in a.k1.split(",") if x != ""]:
+    _lib.set_tuning("k1_cfg", cfg)
+    for _ in range(3):
+        env.get_after_states(out=(feats, valid, count))
+    ms = timed(lambda: env.get_after_states(out=(feats, valid, count)), 9)
+    out["k1_cfg%d_ms" % cfg] = ms
+    out["k1_cfg%d_checksum" % cfg] = int(count.sum().item())
+_lib.set_tuning("k1_cfg", -1)
+for cfg in [int(x) for x in a.k3.split(",") if x != ""]:
+    _lib.set_tuning("k3_cfg", cfg)
+    env.state.copy_(saved)
+    env.rollout(32, "greedy")
+    ms = timed(lambda: env.rollout(32, "greedy"), 7)
+    out["k3_cfg%d_ms_per_32" % cfg] = ms
+    out["k3_cfg%d_placements_per_s" % cfg] = n * 32 / (ms * 1e-3)
+_lib.set_tuning("k3_cfg", -1)
+env.state.copy_(saved)
+a0 = torch.zeros(n, dtype=torch.int32, device="cuda")
+for _ in range(2):
+    env.step(a0, auto_reset=True, check=False)
+env.state.copy_(saved)
+out["k2_ms"] = timed(lambda: env.step(a0, auto_reset=True, check=False), 5)
+envr = BatchedTetris(C, R, n, piece_set=1, seed=7)
+envr.rollout(30, "random")
+out["k3r_ms_per_32"] = timed(lambda: envr.rollout(32, "random"), 5)
+print(json.dumps(out))

@@ -17,6 +17,7 @@ import subprocess
 import sys
 import tempfile
 
+DEPTH = int(os.environ.get("NCU_LINES_DEPTH", "1"))   # 0: the __global__ function's line; 1: one inlining level below
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.environ.get("TB_SO_PATH") or os.path.join(ROOT, "tetris_b200", "csrc", "libtetris_b200.so")
 
@@ -25,8 +26,8 @@ def disasm_chains(kernel_sub):
     """offset -> [(file, line) innermost .. outermost]"""
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", SO], cwd=tmp, stdout=subprocess.DEVNULL)
-    txt = []                                   # one cubin per translation unit (board shape): scan them all
-    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    txt = []                                   # one cubin per translation unit (board shape, distinct names): scan them all
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin") and "sm_100" in f):
         txt += subprocess.run(["nvdisasm", "--print-line-info-inline", "-c", os.path.join(tmp, cubin)],
                               capture_output=True, text=True).stdout.splitlines()
     out, chain, fresh, active = {}, [], True, False
@@ -85,6 +86,8 @@ def main():
         chain, text = chains.get(off, ([("?", 0)], r[1]))
         inner = chain[0] if chain else ("?", 0)
         outer = chain[-1] if chain else ("?", 0)
+        if DEPTH and len(chain) > DEPTH:
+            outer = chain[-1 - DEPTH]          # the line inside the body function the kernel wraps (phase attribution)
         for d, k in ((by_line, inner), (by_outer, outer)):
             d[k][0] += inst; d[k][1] += thr; d[k][2] += smp
         op = text.split()[0] if not text.startswith("@") else text.split()[1]

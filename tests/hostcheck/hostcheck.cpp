@@ -17,7 +17,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
     for (int r = 0; r < S::N; ++r) w[r >> 1] |= (uint32_t)rows[r] << (16 * (r & 1));
     uint32_t col[C];
     rows_to_cols<C, R>(w, col);
-    static uint16_t runtab[RunTab<R>::SIZE];
+    static uint32_t runtab[RunTab<R>::SIZE];
     static bool init = false;
     if (!init) { for (int m = 0; m < RunTab<R>::SIZE; ++m) runtab[m] = run_tab_entry<R>((uint32_t)m); init = true; }
     uint32_t rec[Env<C, R>::WORDS + 8];
@@ -124,11 +124,11 @@ extern "C" int hc_table_images()
     static constexpr OdescImage od = make_odesc_image();
     for (int i = 0; i < kNumOris; ++i) {
         const OriU u = decode_ori(kOriHost[i]);
-        uint32_t w[27];
+        uint32_t w[31];
         std::memcpy(w, &u, sizeof w);
-        for (int k = 0; k < 27; ++k)
+        for (int k = 0; k < 31; ++k)
             if (od.w[i][k] != w[k]) return -(100 + i);
-        if (od.w[i][27] != 0u) return -(200 + i);
+        if (od.w[i][31] != 0u) return -(200 + i);
     }
     if (!run_image_ok<20>()) return -20;
     if (!run_image_ok<10>()) return -10;

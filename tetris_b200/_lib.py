@@ -51,6 +51,18 @@ def _shape_obj(c, r):
     return os.path.join(BUILD_DIR, "tb_shape_%dx%d.o" % (c, r))
 
 
+def _shape_stub(c, r, plugin=False):
+    """A two-line translation unit per shape, so that every shape's cubin carries its own name inside the library
+    (cuobjdump / nvdisasm / ncu tell them apart): build/tb_shape_<C>x<R>.cu."""
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    path = os.path.join(BUILD_DIR, "tb_shape_%dx%d%s.cu" % (c, r, "_plugin" if plugin else ""))
+    text = "#define TB_C %d\n#define TB_R %d\n%s#include \"tb_shape.cu\"\n" % (
+        c, r, "#define TB_SHAPE_PLUGIN 1\n" if plugin else "")
+    if not os.path.exists(path) or open(path).read() != text:
+        open(path, "w").write(text)
+    return path
+
+
 def build(force=False, verbose=False, shapes=None):
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU): one object per board
     shape (tb_shape.cu -DTB_C -DTB_R), compiled in parallel, plus the ABI object, linked into libtetris_b200.so."""
@@ -63,8 +75,7 @@ def build(force=False, verbose=False, shapes=None):
     for (c, r) in shapes:
         obj = _shape_obj(c, r)
         if force or _newer(SHAPE_DEPS, obj):
-            jobs.append((obj, [_nvcc()] + NVCC_FLAGS + extra + ["-DTB_C=%d" % c, "-DTB_R=%d" % r, "-c", "-o", obj,
-                                                                os.path.join(CSRC, "tb_shape.cu")]))
+            jobs.append((obj, [_nvcc()] + NVCC_FLAGS + extra + ["-I", CSRC, "-c", "-o", obj, _shape_stub(c, r)]))
     abi_obj = os.path.join(BUILD_DIR, "tb_abi.o")
     # the list of linked-in shapes is a generated header of the ABI object: rewritten only when the list changes
     inc = os.path.join(BUILD_DIR, "tb_builtin_shapes.inc")
@@ -95,6 +106,26 @@ def build(force=False, verbose=False, shapes=None):
     return SO_PATH
 
 
+def build_variant(path, defines=(), shapes=((10, 20),)):
+    """Experiments: a second library with extra -D flags (A/B runs load it through TB_SO_PATH)."""
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    inc = os.path.join(tmp, "shapes.h")
+    open(inc, "w").write("#define TB_BUILTIN_SHAPES(X) " + " ".join("X(%d, %d)" % s for s in shapes) + "\n")
+    objs, procs = [], []
+    for (c, r) in shapes:
+        obj = os.path.join(tmp, "shape_%dx%d.o" % (c, r))
+        objs.append(obj)
+        procs.append(subprocess.Popen([_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] +
+                                      ["-DTB_C=%d" % c, "-DTB_R=%d" % r, "-c", "-o", obj, os.path.join(CSRC, "tb_shape.cu")]))
+    abi = os.path.join(tmp, "abi.o")
+    procs.append(subprocess.Popen([_nvcc()] + NVCC_FLAGS + ["-include", inc, "-c", "-o", abi, os.path.join(CSRC, "tb_abi.cu")]))
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("variant build failed")
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", path] + objs + [abi, "-ldl"])
+    return path
+
+
 def shape_plugin_path(c, r):
     return os.path.join(CSRC, "libtb_shape_%dx%d.so" % (c, r))
 
@@ -106,8 +137,8 @@ def build_shape(c, r, force=False):
         raise ValueError("board shape %dx%d is outside 4..16 columns x 4..28 rows (uint16 row masks, 32-bit column masks)" % (c, r))
     path = shape_plugin_path(c, r)
     if force or _newer(SHAPE_DEPS, path):
-        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-shared", "-DTB_SHAPE_PLUGIN", "-DTB_C=%d" % c, "-DTB_R=%d" % r,
-                                                       "-o", path, os.path.join(CSRC, "tb_shape.cu")], cwd=CSRC)
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-shared", "-I", CSRC, "-o", path, _shape_stub(c, r, plugin=True)],
+                              cwd=CSRC)
     return path
 
 

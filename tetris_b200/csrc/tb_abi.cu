@@ -127,7 +127,7 @@ using namespace tb;
 // 32-bit column masks).  Any other shape with 4 <= C <= 16, 4 <= R <= 28 can be compiled into its own shared object
 // (tetris_b200._lib.build_shape) and added with tb_load_shape().
 // The list is generated by the build (tetris_b200/_lib.py: BUILTIN_SHAPES -> build/tb_builtin_shapes.inc).
-#if __has_include("build/tb_builtin_shapes.inc")
+#if !defined(TB_BUILTIN_SHAPES) && __has_include("build/tb_builtin_shapes.inc")
 #include "build/tb_builtin_shapes.inc"
 #endif
 #ifndef TB_BUILTIN_SHAPES

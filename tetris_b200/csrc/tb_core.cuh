@@ -460,35 +460,61 @@ TB_HD void eval_slow(const uint32_t *col, uint32_t d, int c, Eval &e, uint32_t *
 }
 
 // ---------------------------------------------------------------------------------------------
-// run-sum by table.  A well mask of a non-terminal board has bits only below row R, so it splits into two halves
-// of HB = ceil(R / 2) bits; the table has 2^HB uint16 entries, entry for a half m = run_sum(m) | trail << 8 |
-// lead << 12 where trail / lead = length of the run of ones touching the half's bit 0 / bit HB-1.  A column is two
-// lookups plus the cross term of a run spanning the halves: (p+q)(p+q+1)/2 = p(p+1)/2 + q(q+1)/2 + p*q.
-// No POPC, no data-dependent loop.
+// run-sum by table.  A well mask of a non-terminal board has bits only below row R.  It is cut into NCH chunks of
+// HB = ceil(R / NCH) bits (1 chunk up to R = 10, 2 up to R = 20, 3 above); the table has 2^HB 32-bit entries, entry
+// for a chunk m = run_sum(m) | lead << 8 | trail << 16 | 1 << 24, where trail / lead = length of the run of ones
+// touching the chunk's bit 0 / bit HB-1.  A run spanning two chunks adds the cross term of
+// (p+q)(p+q+1)/2 = p(p+1)/2 + q(q+1)/2 + p*q, so for two chunks
+//     run_sum = rs0 * 1 + lead0 * trail1 + trail0 * 0 + 1 * rs1
+// which is ONE dot-product instruction (IDP.4A) on the low entry and a byte-permuted high entry.
+// No POPC, no data-dependent loop, no warp vote: the same code on every board.
 // ---------------------------------------------------------------------------------------------
 template <int R>
 struct RunTab {
-    static constexpr int HB = (R + 1) / 2;
+    static constexpr int NCH = R <= 10 ? 1 : (R <= 20 ? 2 : 3);
+    static constexpr int HB = (R + NCH - 1) / NCH;
     static constexpr int SIZE = 1 << HB;
-    static_assert(HB <= 12, "run table entries hold runs of at most 15 cells");
+    static_assert(HB <= 10 && R <= 28, "run table: chunks of at most 10 rows, boards of at most 28 rows");
 };
 template <int R>
-TB_HD uint16_t run_tab_entry(uint32_t m)
+TB_HD uint32_t run_tab_entry(uint32_t m)
 {
     constexpr int HB = RunTab<R>::HB;
     const int rs = run_sum(m);
-    const uint32_t z = ~m & mask_lo(HB);                           // the zero bits of the half
+    const uint32_t z = ~m & mask_lo(HB);                           // the zero bits of the chunk
     const int trail = z ? ctz32(z) : HB;                           // ones below the lowest zero
     const int lead = z ? clz32(z) - (32 - HB) : HB;                // ones above the highest zero
-    return (uint16_t)(rs | (trail << 8) | (lead << 12));
+    return (uint32_t)rs | ((uint32_t)lead << 8) | ((uint32_t)trail << 16) | (1u << 24);
+}
+TB_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __dp4a(a, b, c);
+#else
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+    return c;
+#endif
+}
+// acc + run_sum(w), w < 2^R
+template <int R>
+TB_HD uint32_t run_sum_acc(const uint32_t *tab, uint32_t w, uint32_t acc)
+{
+    constexpr int HB = RunTab<R>::HB, NCH = RunTab<R>::NCH;
+    constexpr uint32_t M = (uint32_t)(RunTab<R>::SIZE - 1);
+    if (NCH == 1) return acc + (tab[w] & 255u);
+    const uint32_t e0 = tab[w & M], e1 = tab[(w >> HB) & M];
+    // e1 permuted to bytes [1, trail1, 0, rs1] against e0 = [rs0, lead0, trail0, 1]
+    acc = dp4a_u(e0, prmt(e1, 0u, 0x0423), acc);
+    if (NCH == 3) {
+        const uint32_t e2 = tab[w >> (2 * HB)];
+        const uint32_t lead0 = (e0 >> 8) & 255u, lead1 = (e1 >> 8) & 255u, trail1 = (e1 >> 16) & 255u;
+        const uint32_t carry = trail1 == (uint32_t)HB ? lead0 + (uint32_t)HB : lead1;   // run reaching chunk 2 from below
+        acc += (e2 & 255u) + carry * ((e2 >> 16) & 255u);
+    }
+    return acc;
 }
 template <int R>
-TB_HD int run_sum_tab(const uint16_t *tab, uint32_t w)   // w < 2^R
-{
-    constexpr int HB = RunTab<R>::HB;
-    const uint32_t e0 = tab[w & (uint32_t)(RunTab<R>::SIZE - 1)], e1 = tab[w >> HB];
-    return (int)(((e0 + e1) & 127u) + (e0 >> 12) * ((e1 >> 8) & 15u));   // run sums of the halves total < 128
-}
+TB_HD int run_sum_tab(const uint32_t *tab, uint32_t w) { return (int)run_sum_acc<R>(tab, w, 0u); }
 
 // Small non-negative int -> float without the conversion unit: the bit pattern 0x4B000000 + v is the float
 // 2^23 + v.  The env record keeps its totals already biased, so adding a placement's integer delta yields the
@@ -514,24 +540,28 @@ TB_HD float u2f(int v) { return unbias(kFloatBias + (uint32_t)v); }
 template <int C, int R>
 struct Env {
     static constexpr int COLX = 0;                         // C+4 words: [k] = column k-2; walls (ALL) at -1 and C, 0 at -2, C+1
-    static constexpr int PAND = COLX + C + 4;              // C+1 words: AND of columns < c
-    static constexpr int SAND = PAND + C + 1;              // C+1 words: AND of columns >= c
-    static constexpr int H8 = SAND + C + 1;                // C+2 bytes: [k] = height of column k-1 (walls: R)
-    static constexpr int NR8 = H8 + (C + 2 + 3) / 4;       // C bytes: hole runs per column
-    static constexpr int PW16 = NR8 + (C + 3) / 4;         // C+3 u16: [i] = wells of columns < clamp(i-1, 0, C)
+    static constexpr int FQ = COLX + C + 4;                // 4 words: [q-1] = rows with exactly q empty cells, q = 1..4
+    static constexpr int H8 = FQ + 4;                      // C+2 bytes: [k] = height of column k-1 (walls: R)
+    static constexpr int NR8 = H8 + (C + 2 + 3) / 4;       // C bytes: hole runs per column; byte C: tallest column
+    static constexpr int PW16 = NR8 + (C + 1 + 3) / 4;     // C+3 u16: [i] = wells of columns < clamp(i-1, 0, C)
     static constexpr int PRT16 = PW16 + (C + 3 + 1) / 2;   // C+2 u16: [i] = row transitions of columns < min(i, C)
-    static constexpr int TOT = PRT16 + (C + 2 + 1) / 2;    // ct, hd, wells, rt, holes (each + kFloatBias), hole-row mask, hmax
+    static constexpr int TOT = PRT16 + (C + 2 + 1) / 2;    // ct, hd, wells, rt, holes (each + kFloatBias), hole-row mask
     static constexpr int T_CT = TOT + 0, T_HD = TOT + 1, T_WELLS = TOT + 2, T_RT = TOT + 3,
-                         T_HOLES = TOT + 4, T_HM = TOT + 5, T_HMAX = TOT + 6;
-    static constexpr int WORDS_RAW = TOT + 7;
-    static constexpr int WORDS = WORDS_RAW | 1;            // odd stride: records of different envs spread over banks
+                         T_HOLES = TOT + 4, T_HM = TOT + 5;
+    static constexpr int B_HMAX = 4 * NR8 + C;             // byte index of the tallest column's height
+    static constexpr int WORDS_RAW = TOT + 6;
+    // Record stride in words.  Odd, so that thread t working on record t is conflict-free whatever the field.  For
+    // C = 10 the natural size is 43 = 32 + 11: the records of three envs at consecutive positions start 11 banks apart
+    // and those of four envs at positions 8 apart start 8 banks apart -- what makes the windows of the tile kernels
+    // (3 envs x 9-10 anchor columns, 4 envs x 7-8) free of shared-memory bank conflicts (tb_kernels.cuh, window_slot).
+    static constexpr int WORDS = WORDS_RAW | 1;
 };
 
 // Builds the record from the columns already stored in rec[COLX + 2 .. COLX + 2 + C).  A rolled loop on purpose: an
 // unrolled builder is 8x the code, and instruction-cache footprint matters more than a few extra shared-memory
 // accesses (K1 / K3 are instruction-latency bound).  Precondition: every column height is <= R (non-terminal state).
 template <int C, int R>
-TB_HD void build_env(const uint16_t *runtab, uint32_t *rec)
+TB_HD void build_env(const uint32_t *runtab, uint32_t *rec)
 {
     using S = Shape<C, R>;
     using K = Env<C, R>;
@@ -541,14 +571,21 @@ TB_HD void build_env(const uint16_t *runtab, uint32_t *rec)
     rec[K::COLX + C + 2] = S::ALL; rec[K::COLX + C + 3] = 0u;
     rb[4 * K::H8 + 0] = (uint8_t)R; rb[4 * K::H8 + C + 1] = (uint8_t)R;
     rh[2 * K::PW16 + 0] = 0; rh[2 * K::PW16 + 1] = 0; rh[2 * K::PRT16 + 0] = 0;
-    int holes = 0, ct = 0, hd = 0, wells = 0, rt = 0, hL = R;
-    uint32_t hm = 0, L = S::ALL, any = 0, acc = S::ALL;
+    int holes = 0, ct = 0, hd = 0, rt = 0, hL = R;
+    uint32_t wells = 0;
+    uint32_t hm = 0, L = S::ALL, any = 0;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;                       // bit-sliced count of empty cells per row (c3: >= 8)
     uint32_t x = rec[K::COLX + 2];
 #pragma unroll 1
     for (int c = 0; c < C; ++c) {
         const uint32_t Rt = rec[K::COLX + 3 + c];                  // column c + 1, or the right wall sentinel
-        rec[K::PAND + c] = acc;
-        acc &= x;
+        {
+            const uint32_t e = ~x;
+            const uint32_t k0 = c0 & e; c0 ^= e;
+            const uint32_t k1 = c1 & k0; c1 ^= k0;
+            const uint32_t k2 = c2 & k1; c2 ^= k1;
+            c3 |= k2;
+        }
         const int h = height_of(x);
         const uint32_t mh = mask_lo(h);
         const uint32_t hole = ~x & mh;
@@ -559,7 +596,7 @@ TB_HD void build_env(const uint16_t *runtab, uint32_t *rec)
         const int nr = popc32(t);
         ct += 1 + 2 * nr;
         while (t) { const int r = ctz32(t); hd += popc32(x >> (r + 1)); t &= t - 1; }
-        wells += run_sum_tab<R>(runtab, L & Rt & ~x);
+        wells = run_sum_acc<R>(runtab, L & Rt & ~x, wells);
         if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh);
         else rt += popc32(L & mask_lo(hL));
         rb[4 * K::H8 + c + 1] = (uint8_t)h;
@@ -568,18 +605,21 @@ TB_HD void build_env(const uint16_t *runtab, uint32_t *rec)
         rh[2 * K::PRT16 + c + 1] = (uint16_t)rt;
         L = x; hL = h; x = Rt;
     }
-    rec[K::PAND + C] = acc;
     rh[2 * K::PW16 + C + 2] = (uint16_t)wells;
     rh[2 * K::PRT16 + C + 1] = (uint16_t)rt;
     rt += R - popc32(L);                                           // L = column C-1 after the loop
-    acc = S::ALL;
-    rec[K::SAND + C] = acc;
-#pragma unroll 1
-    for (int c = C - 1; c >= 0; --c) { acc &= rec[K::COLX + 2 + c]; rec[K::SAND + c] = acc; }
+    // Full-row detection without looking at the other columns: every cell of a dropped piece lands on an EMPTY cell
+    // (above its column's height), so a changed row becomes full exactly when its number of empty cells equals the
+    // number of piece cells the orientation puts into it (pieces_per_changed_row, 1..4).  state.py:122-124 restated.
+    const uint32_t lo3 = ~c3;
+    rec[K::FQ + 0] = c0 & ~c1 & ~c2 & lo3;
+    rec[K::FQ + 1] = ~c0 & c1 & ~c2 & lo3;
+    rec[K::FQ + 2] = c0 & c1 & ~c2 & lo3;
+    rec[K::FQ + 3] = ~c0 & ~c1 & c2 & lo3;
     rec[K::T_CT] = kFloatBias + (uint32_t)ct; rec[K::T_HD] = kFloatBias + (uint32_t)hd;
-    rec[K::T_WELLS] = kFloatBias + (uint32_t)wells; rec[K::T_RT] = kFloatBias + (uint32_t)rt;
+    rec[K::T_WELLS] = kFloatBias + wells; rec[K::T_RT] = kFloatBias + (uint32_t)rt;
     rec[K::T_HOLES] = kFloatBias + (uint32_t)holes; rec[K::T_HM] = hm;
-    rec[K::T_HMAX] = (uint32_t)height_of(any);
+    rb[K::B_HMAX] = (uint8_t)height_of(any);
 }
 
 // eval_placement status
@@ -592,7 +632,6 @@ constexpr int kFastTerminal = 2;  // no line clears and the piece reaches row R:
 template <int C, int R, int W>
 struct Neigh {
     uint32_t y[W + 4];       // columns c-2 .. c+W+1
-    uint32_t frame;          // AND of the columns outside c .. c+W-1 (rows that are full but for the piece's columns)
     uint32_t mh[W + 1];      // mask_lo(height) of columns c .. c+W
     int h[W + 2];            // heights of columns c-1 .. c+W
     int nr[W];               // hole runs of columns c .. c+W-1
@@ -612,7 +651,6 @@ TB_HD void load_neigh(const uint32_t *rec, int c, Neigh<C, R, W> &nb)
     for (int k = 0; k < W; ++k) nb.nr[k] = (int)rb[4 * K::NR8 + c + k];
 #pragma unroll
     for (int k = 0; k < W + 1; ++k) nb.mh[k] = mask_lo(nb.h[1 + k]);
-    nb.frame = rec[K::PAND + c] & rec[K::SAND + c + W];
     nb.wells0 = rec[K::T_WELLS] - ((uint32_t)rh[2 * K::PW16 + c + W + 2] - (uint32_t)rh[2 * K::PW16 + c]);
     nb.rt0 = rec[K::T_RT] - ((uint32_t)rh[2 * K::PRT16 + c + W + 1] - (uint32_t)rh[2 * K::PRT16 + c]);
 }
@@ -626,8 +664,12 @@ struct OriU {
     uint32_t chgm;                // mask_lo(len(changed_lines))
     int ph;                       // piece height
     uint32_t lh2;                 // 2 + 2 * landing_height_bonus + kFloatBias
+    // pieces_per_changed_row takes at most two distinct values qa, qb over an orientation's changed rows:
+    // qa1 / qb1 = value - 1 (index of the record's FQ word), ma / mb = the changed rows (relative to the anchor) with
+    // that many piece cells.  One value only: qb1 = qa1, mb = 0.
+    uint32_t qa1, ma, qb1, mb;
 };
-constexpr int kOriWords = 28;     // OriU as flat words: bot[4] len[4] top[4] seg[4] mbot[4] mtop[4] chgm ph lh2 pad
+constexpr int kOriWords = 32;     // OriU as flat words: bot[4] len[4] top[4] seg[4] mbot[4] mtop[4] chgm ph lh2 qa1 ma qb1 mb pad
 TB_HD OriU decode_ori(uint32_t d)
 {
     OriU u;
@@ -643,9 +685,18 @@ TB_HD OriU decode_ori(uint32_t d)
     u.chgm = mask_lo(desc_chg(d));
     u.ph = desc_ph(d);
     u.lh2 = 2u + (uint32_t)desc_bonus2(d) + kFloatBias;
+    // pieces_per_changed_row of row k = number of piece columns whose cells cover relative row k
+    u.qa1 = 0u; u.ma = 0u; u.qb1 = 0u; u.mb = 0u;
+    for (int k = 0; k < desc_chg(d); ++k) {
+        uint32_t q = 0;
+        for (int dx = 0; dx < 4; ++dx) q += (u.seg[dx] >> k) & 1u;
+        if (u.ma == 0u || u.qa1 == q - 1u) { u.qa1 = q - 1u; u.ma |= 1u << k; }
+        else { u.qb1 = q - 1u; u.mb |= 1u << k; }
+    }
+    if (u.mb == 0u) u.qb1 = u.qa1;
     return u;
 }
-static_assert(sizeof(OriU) == 27 * 4, "OriU is 27 words");
+static_assert(sizeof(OriU) == 31 * 4, "OriU is 31 words");
 
 // ---------------------------------------------------------------------------------------------
 // Compile-time images of the two tables the tile kernels keep in shared memory:
@@ -669,12 +720,21 @@ constexpr OdescImage make_odesc_image()
         t.w[i][24] = cx_mask((int)((d >> 23) & 7u));                 // chgm
         t.w[i][25] = (d >> 28) & 7u;                                 // ph
         t.w[i][26] = 2u + ((d >> 26) & 3u) + kFloatBias;             // lh2
-        t.w[i][27] = 0u;
+        uint32_t qa1 = 0, ma = 0, qb1 = 0, mb = 0;
+        for (uint32_t k = 0; k < ((d >> 23) & 7u); ++k) {
+            uint32_t q = 0;
+            for (int dx = 0; dx < 4; ++dx) q += (t.w[i][12 + dx] >> k) & 1u;
+            if (ma == 0u || qa1 == q - 1u) { qa1 = q - 1u; ma |= 1u << k; }
+            else { qb1 = q - 1u; mb |= 1u << k; }
+        }
+        if (mb == 0u) qb1 = qa1;
+        t.w[i][27] = qa1; t.w[i][28] = ma; t.w[i][29] = qb1; t.w[i][30] = mb;
+        t.w[i][31] = 0u;
     }
     return t;
 }
 
-template <int R> struct RunImage { alignas(16) uint16_t v[RunTab<R>::SIZE]; };
+template <int R> struct RunImage { alignas(16) uint32_t v[RunTab<R>::SIZE]; };
 template <int R>
 constexpr RunImage<R> make_run_image()
 {
@@ -687,7 +747,7 @@ constexpr RunImage<R> make_run_image()
         int trail = 0, lead = 0;
         while (trail < HB && ((m >> trail) & 1)) ++trail;
         while (lead < HB && ((m >> (HB - 1 - lead)) & 1)) ++lead;
-        t.v[m] = (uint16_t)(rs | (trail << 8) | (lead << 12));
+        t.v[m] = (uint32_t)rs | ((uint32_t)lead << 8) | ((uint32_t)trail << 16) | (1u << 24);
     }
     return t;
 }
@@ -695,10 +755,8 @@ constexpr RunImage<R> make_run_image()
 // Incremental evaluation of one placement: orientation `u` (width W) anchored at column c.  Only the piece's
 // columns and their neighbours are re-evaluated; everything else comes from the env record.  Branch-free apart
 // from the two early exits.
-// LOWHALF (device only): when no lane of the warp has a well cell in the upper half of the board -- the usual case on
-// boards under greedy play -- the cumulative-wells lookups reduce to one table access per column.
-template <int C, int R, int W, bool LOWHALF = false>
-TB_HD int eval_neigh(const uint32_t *rec, const uint16_t *runtab, const Neigh<C, R, W> &nb, const OriU &u, int c, Eval &e)
+template <int C, int R, int W>
+TB_HD int eval_neigh(const uint32_t *rec, const uint32_t *runtab, const Neigh<C, R, W> &nb, const OriU &u, int c, Eval &e)
 {
     using K = Env<C, R>;
     int h[W + 2];
@@ -711,16 +769,28 @@ TB_HD int eval_neigh(const uint32_t *rec, const uint16_t *runtab, const Neigh<C,
 #pragma unroll
     for (int dx = 0; dx < W; ++dx) a = imax(a, h[1 + dx] - u.bot[dx]);          // tetromino.py: anchor_row = max(h - bottom)
 
+    // rows among changed_lines that the placement completes: empty cells before == piece cells added (see build_env)
+    const uint32_t full = (rec[K::FQ + u.qa1] & (u.ma << a)) | (rec[K::FQ + u.qb1] & (u.mb << a));
+    const int top = a + u.ph;
+    e.a = a; e.full = full;
+    if (full != 0u) {
+        // stack rows are contiguous, so clearing k rows lowers the tallest column by exactly k (SURVEY Appendix A)
+        const int hmax = (int)reinterpret_cast<const uint8_t *>(rec)[K::B_HMAX];
+        e.terminal = (imax(hmax, top) - popc32(full)) > R;
+        return kFastClears;
+    }
+    if (top > R) { e.terminal = 1; return kFastTerminal; }
+    e.terminal = 0;
+
     const uint32_t ma = mask_lo(a);
     int gapsum = 0, gapcnt = 0, hdadd = 0;
-    uint32_t gapor = 0, fp = nb.frame;
+    uint32_t gapor = 0;
     uint32_t mt[W];                                                // mask_lo(new height) of the piece columns
 #pragma unroll
     for (int dx = 0; dx < W; ++dx) {
         const int len = u.len[dx], lo = a + u.bot[dx], hh = h[1 + dx];
         const int g = lo - hh;                                     // new holes under the piece in this column
         y[2 + dx] |= u.seg[dx] << a;
-        fp &= y[2 + dx];
         gapsum += g;
         gapcnt += (g > 0);
         gapor |= ((ma << u.bot[dx]) | u.mbot[dx]) ^ nb.mh[dx];     // rows hh .. lo-1
@@ -728,37 +798,13 @@ TB_HD int eval_neigh(const uint32_t *rec, const uint16_t *runtab, const Neigh<C,
         h[1 + dx] = lo + len;
         mt[dx] = (ma << u.top[dx]) | u.mtop[dx];
     }
-    const uint32_t full = fp & (u.chgm << a);
-    const int top = a + u.ph;
-    e.a = a; e.full = full;
-    if (full != 0u) {
-        // stack rows are contiguous, so clearing k rows lowers the tallest column by exactly k (SURVEY Appendix A)
-        e.terminal = (imax((int)rec[K::T_HMAX], top) - popc32(full)) > R;
-        return kFastClears;
-    }
-    if (top > R) { e.terminal = 1; return kFastTerminal; }
-    e.terminal = 0;
 
     // wells over columns c-1 .. c+W, row transitions over columns c .. c+W; the sentinels make the walls come out right
     uint32_t wells = nb.wells0, rt = nb.rt0;
-#if defined(__CUDA_ARCH__)
-    if (LOWHALF) {
-        uint32_t wm[W + 2], hi = 0u;
 #pragma unroll
-        for (int k = 1; k <= W + 2; ++k) { wm[k - 1] = y[k - 1] & y[k + 1] & ~y[k]; hi |= wm[k - 1]; }
-        if (__any_sync(__activemask(), (hi >> RunTab<R>::HB) != 0u)) {
-#pragma unroll
-            for (int k = 0; k < W + 2; ++k) wells += (uint32_t)run_sum_tab<R>(runtab, wm[k]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < W + 2; ++k) wells += (uint32_t)(runtab[wm[k]] & 127u);
-        }
-    } else
-#endif
-    {
-#pragma unroll
-        for (int k = 1; k <= W + 2; ++k) wells += (uint32_t)run_sum_tab<R>(runtab, y[k - 1] & y[k + 1] & ~y[k]);
-    }
+    for (int k = 1; k <= W + 2; ++k) wells = run_sum_acc<R>(runtab, y[k - 1] & y[k + 1] & ~y[k], wells);
+    // (skipping the lookups of a column when no lane of the warp has a well cell there -- a vote per column -- was
+    //  measured 8 % slower in K1 and 7 % in K3: profiles/README.md, r2c)
 #pragma unroll
     for (int dx = 0; dx < W; ++dx) {                               // piece columns: height > 0
         const int hj = h[1 + dx], hl = h[dx];
@@ -782,7 +828,7 @@ TB_HD int eval_neigh(const uint32_t *rec, const uint16_t *runtab, const Neigh<C,
 }
 
 template <int C, int R, int W>
-TB_HD int eval_placement(const uint32_t *rec, const uint16_t *runtab, uint32_t d, int c, Eval &e)
+TB_HD int eval_placement(const uint32_t *rec, const uint32_t *runtab, uint32_t d, int c, Eval &e)
 {
     Neigh<C, R, W> nb;
     load_neigh<C, R, W>(rec, c, nb);
@@ -791,7 +837,7 @@ TB_HD int eval_placement(const uint32_t *rec, const uint16_t *runtab, uint32_t d
 
 // width dispatch (W is warp-uniform in the kernels)
 template <int C, int R>
-TB_HD int eval_placement_w(const uint32_t *rec, const uint16_t *runtab, uint32_t d, int c, Eval &e)
+TB_HD int eval_placement_w(const uint32_t *rec, const uint32_t *runtab, uint32_t d, int c, Eval &e)
 {
     switch (desc_w(d)) {
     case 1: return eval_placement<C, R, 1>(rec, runtab, d, c, e);

@@ -182,40 +182,47 @@ k_reset(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const ui
 // K1 afterstates.
 //
 // A CTA owns a tile of TILE envs (template parameter; THREADS = TILE threads in the throughput configuration, a multiple
-// of TILE in the small-batch ones).  Phase A (thread per env): load + transpose the board, build the env
-// record in shared memory, append the env to the list of its piece.  Phase B (warp per window): all lanes of a
-// warp work on envs holding the SAME piece -- lane = (env k of the window, anchor column c) -- and walk the piece's
-// orientations in a warp-uniform loop, so the orientation descriptor is uniform, every loop over the piece's
-// columns has a uniform trip count, and the neighbourhood loads are shared by the orientations of a column loop.
-// Placements that clear a line only need the general evaluation for their FEATURES (legality follows from the
-// full-row count); they are marked in per-env bit masks and evaluated one lane per item in phase S.
+// of TILE in the small-batch ones).
+//   Phase A (thread per env): counting sort of the tile's envs by piece -- the env's rank within its piece by a
+//     shared atomic, barrier, slot = (envs with smaller pieces) + rank -- then load + transpose the board and build the
+//     env record in shared memory AT ITS SLOT.
+//   Phase B (warp per window): all lanes of a warp work on envs holding the SAME piece -- lane = (env k of the window,
+//     anchor column c) -- and walk the piece's orientations in a warp-uniform loop, so the orientation descriptor is
+//     uniform, every loop over the piece's columns has a uniform trip count, and the neighbourhood loads are shared by the
+//     orientations of a column loop.  Because same-piece envs sit in consecutive slots, a window's records are at fixed
+//     distances, chosen (window_stride) so that they start on disjoint ranges of shared-memory banks: the window's loads
+//     are conflict-free (round 1 indexed records by env id: 37 % of K1's shared wavefronts were conflict replays).
+//   Phase S: placements that clear a line only need the general evaluation for their FEATURES (legality follows from the
+//     full-row count); they are marked in per-slot bit masks in phase B and evaluated one lane per item.
 // ---------------------------------------------------------------------------------------------
 constexpr int kNumJobs = 2 * kNumPieces;
+constexpr int kNoSlot = 0xFFFF;
 
 template <int C, int R, int TILE>
 struct CtaSmem {
     using K = Env<C, R>;
-    uint32_t rec[TILE * K::WORDS];
+    static_assert(TILE <= 256, "slot -> env map is bytes");
+    uint32_t rec[TILE * K::WORDS];       // env records by SLOT (the tile's envs sorted by piece)
     alignas(16) uint32_t odesc[kNumOris][kOriWords]; // orientation descriptors, decoded (OriU): broadcast 128-bit loads
-    uint32_t vloc[TILE][2];              // K1: legal placements of each env per column loop (16 bits per orientation)
-                                         // K3: best orderable score of each env per column loop
-    uint32_t sloc[TILE][2];              // placements of each env that need the general evaluation (they clear a line),
+    uint32_t vloc[TILE][2];              // by slot.  K1: legal placements per column loop (16 bits per orientation)
+                                         //           K3: best orderable score per column loop
+    uint32_t sloc[TILE][2];              // by slot: placements that need the general evaluation (they clear a line),
                                          // per column loop, same bit layout as vloc in K1 (16 bits per orientation)
-    alignas(16) uint16_t run[RunTab<R>::SIZE];
-    uint8_t list[kNumPieces][TILE];      // tile-local env indices grouped by piece
-    uint8_t pid[TILE];                   // piece of each env of the tile
+    alignas(16) uint32_t run[RunTab<R>::SIZE];
+    uint16_t slot_of[TILE];              // env (thread of the tile) -> slot; kNoSlot: the env takes no part
+    uint8_t env_of[TILE];                // slot -> env (thread of the tile)
+    uint8_t pid[TILE];                   // by slot: piece
     int cnt[2][kNumPieces + 1];          // envs per piece, double-buffered by tile / step parity
     uint32_t job[kNumJobs];              // (piece, column loop): p | l << 4 | w << 5 | n << 8 | ob << 10 | sbase << 16
     uint32_t ori[32], piece[16];
 };
-// K3 only (2 CTAs per SM, shared memory to spare): best (score, slot) key among the line-clearing placements,
-// and per-warp episode statistics
-static_assert(sizeof(CtaSmem<10, 20, 256>) <= 76800, "K1 at 10x20 must keep fitting three 256-env CTAs per SM");
+static_assert(sizeof(CtaSmem<10, 20, 256>) <= 57 * 1024, "K1 / K3 at 10x20: four 256-env CTAs per SM fit in shared memory");
 
+// K3 only: best (score, slot) key among the line-clearing placements, and per-warp episode statistics
 template <int TILE, int THREADS = TILE> struct BestSmem {
-    unsigned long long best[TILE];
+    unsigned long long best[TILE];       // by slot
     long long wstat[THREADS / 32][TB_ST_COUNT];
-    uint8_t bslot[TILE][2];              // slot of the best score per column loop
+    uint8_t bslot[TILE][2];              // by slot: enumeration slot of the best score per column loop
 };
 
 // Compile-time images of the two shared-memory tables (tb_core.cuh: make_odesc_image / make_run_image, checked against
@@ -245,23 +252,53 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
         sm.job[threadIdx.x] = jb;
     }
     if (threadIdx.x <= kNumPieces) { sm.cnt[0][threadIdx.x] = 0; sm.cnt[1][threadIdx.x] = 0; }
-    if (RunTab<R>::SIZE % 8 == 0) {
+    if (RunTab<R>::SIZE % 4 == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_run<R>.v);
         uint4 *dst = reinterpret_cast<uint4 *>(sm.run);
-        for (int i = threadIdx.x; i < RunTab<R>::SIZE / 8; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < RunTab<R>::SIZE / 4; i += blockDim.x) dst[i] = src[i];
     } else {
         for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = g_run<R>.v[m];
     }
     __syncthreads();
 }
 
+// Position (within a piece's run of slots) of env k of window `win`.  The records of a window's EPW envs must start on
+// disjoint ranges of shared-memory banks, NC banks each (lane c of an env reads word c + const of its record): with a
+// record stride of `words` (odd), envs at positions D apart are D * words banks apart.  window_stride() finds the
+// smallest such D; windows are then taken from groups of EPW * D consecutive positions (window r of a group = positions
+// r, r + D, .., r + (EPW-1) D).  The ragged end of a piece's run falls back to consecutive positions (a few conflicts,
+// no idle windows).  10x20: records of 43 words; 3 envs x 9..10 columns -> D = 1 (11 banks apart), 4 envs x 7..8
+// columns -> D = 8 (8 banks apart).
+constexpr int window_stride(int epw, int nc, int words)
+{
+    for (int d = 1; d <= 16; ++d) {
+        bool ok = true;
+        for (int i = 0; i < epw && ok; ++i)
+            for (int j = i + 1; j < epw && ok; ++j) {
+                const int diff = ((j - i) * d * words) % 32;
+                if ((diff < 32 - diff ? diff : 32 - diff) < nc) ok = false;
+            }
+        if (ok) return d;
+    }
+    return 1;
+}
+template <int EPW, int NC, int WORDS> struct WinStride { static constexpr int value = window_stride(EPW, NC, WORDS); };
+template <int EPW, int D>
+__device__ __forceinline__ int window_position(int win, int k, int np)
+{
+    if (D == 1) return win * EPW + k;
+    constexpr int G = EPW * D;
+    const int g = win / D, r = win - g * D, b = g * G;
+    return (b + G <= np) ? b + r + D * k : b + EPW * r + k;
+}
+
 // Phase S work distribution.  Every lane owns one env of the warp's 32 and holds that env's slow-placement masks
 // (m0, m1: column loops 0 / 1, bit 16 * o + c).  The set bits of all 32 envs are flattened over the lanes, 32 items per
 // pass, so the general evaluation runs with full warps however the items are spread over the envs.
-// f(owner lane, loop l, orientation o in the loop, column c) is called for every item by one lane.
+// f(owner lane, the owner's `payload`, loop l, orientation o in the loop, column c) is called for every item by one lane.
 // With several warps per 32-env group (small-batch configurations) warp `sub` of `nsub` takes every nsub-th pass.
 template <typename F>
-__device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int lane, int sub, int nsub, F &&f)
+__device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int payload, int lane, int sub, int nsub, F &&f)
 {
     const int cnt = __popc(m0) + __popc(m1);
     int incl = cnt;
@@ -282,11 +319,12 @@ __device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int
         owner &= 31;
         const int before = __shfl_sync(FULLMASK, incl - cnt, owner);
         const uint32_t om0 = __shfl_sync(FULLMASK, m0, owner), om1 = __shfl_sync(FULLMASK, m1, owner);
+        const int opay = __shfl_sync(FULLMASK, payload, owner);
         if (i < total) {
             const int r = i - before, p0 = __popc(om0);
             const int l = r >= p0;
             const int b = (int)__fns(l ? om1 : om0, 0u, (l ? r - p0 : r) + 1);
-            f(owner, l, b >> 4, b & 15);
+            f(owner, opay, l, b >> 4, b & 15);
         }
     }
 }
@@ -316,10 +354,19 @@ __device__ __forceinline__ float *feat_row(float *__restrict__ feats, int64_t en
 
 template <int V> struct IntC { static constexpr int value = V; };
 
+// slot of an env with piece `piece` and rank `rank` among the tile's envs of that piece: envs with smaller pieces first
+__device__ __forceinline__ int slot_from_rank(const int *cnt, int piece, int rank)
+{
+    int base = 0;
+#pragma unroll
+    for (int q = 0; q < kNumPieces - 1; ++q) base += q < piece ? cnt[q] : 0;
+    return base + rank;
+}
+
 // THREADS = CTA size, a multiple of TILE.  THREADS == TILE is the throughput configuration (thread per env in the
-// per-env phases, warp w owns envs 32w .. 32w+31).  THREADS > TILE is the small-batch configuration: the per-env phases
-// use the first TILE threads, phase B spreads the windows over all warps and WPG = THREADS / TILE warps share the
-// phase-S items of each 32-env group, which shortens the critical path of a tile when there are fewer tiles than SMs.
+// per-env phases).  THREADS > TILE is the small-batch configuration: the per-env phases use the first TILE threads,
+// phase B spreads the windows over all warps and WPG = THREADS / TILE warps share the phase-S items of each 32-env
+// group, which shortens the critical path of a tile when there are fewer tiles than SMs.
 template <int C, int R, bool DIRS, int TILE, int THREADS>
 __device__ __forceinline__ void
 afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
@@ -340,42 +387,54 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
         const int64_t e0 = tile * TILE, e = e0 + tid;
         int *cnt = sm.cnt[par];
-        // ---- phase A (thread per env).  cnt[par] was zeroed during the previous tile's phase B.
-        if (env_thread) {
-            sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
-            sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
-        }
+        // ---- phase A1 (thread per env): rank of the env among the tile's envs with the same piece.
+        // cnt[par] was zeroed during the previous tile's phase A2.
+        int piece = kPieceVoid, rank = 0;
         if (env_thread && e < sv.n_env) {
+            piece = unpack_meta(sv.meta[e]).piece;
+            if (piece < kNumPieces) rank = atomicAdd(&cnt[piece], 1);   // finished forks (0xFF / 0xFE): no afterstates
+        }
+        __syncthreads();                                   // counts complete; every warp is done with the previous tile
+        if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
+        // ---- phase A2 (thread per env): the record, at the env's slot
+        int myslot = kNoSlot;
+        if (piece < kNumPieces) {
+            myslot = slot_from_rank(cnt, piece, rank);
             uint32_t col[C];
             load_board<C, R>(sv, e, col);
-            const Meta mt = unpack_meta(sv.meta[e]);
-            uint32_t *myrec = sm.rec + tid * K::WORDS;
+            uint32_t *myrec = sm.rec + myslot * K::WORDS;
 #pragma unroll
             for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
             build_env<C, R>(sm.run, myrec);
-            if (mt.piece < kNumPieces) sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
-            sm.pid[tid] = (uint8_t)min(mt.piece, kNumPieces - 1);       // finished forks (piece 0xFF/0xFE): no afterstates
+            sm.env_of[myslot] = (uint8_t)tid;
+            sm.pid[myslot] = (uint8_t)piece;
+            sm.vloc[myslot][0] = 0u; sm.vloc[myslot][1] = 0u;
+            sm.sloc[myslot][0] = 0u; sm.sloc[myslot][1] = 0u;
         }
+        if (env_thread) sm.slot_of[tid] = (uint16_t)myslot;
         __syncthreads();
-        if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
         // ---- phase B (warp per window): per (piece, column loop) job; a window = EPW envs x (C - W + 1) columns
         // windows are dealt to the warps round robin, continuing across jobs (separately for jobs of 1 and of 2
         // orientations, which cost about 1 : 2), so the warps' totals differ by at most one window per class
         int woff1 = 0, woff2 = 0;
-        auto column_loop = [&](auto wtag, uint32_t jb, int np) {
+        auto column_loop = [&](auto wtag, uint32_t jb, int np, int pbase) {
             constexpr int W = decltype(wtag)::value;
-            constexpr int NC = C - W + 1, EPW = 32 / NC;
+            constexpr int NC = C - W + 1, EPW = 32 / NC, D = WinStride<EPW, NC, K::WORDS>::value;
             const int k = lane / NC, c = lane - k * NC;
             const bool lane_ok = k < EPW;
-            const int p = jb & 15, l = (jb >> 4) & 1, n = (jb >> 8) & 3;
+            const int l = (jb >> 4) & 1, n = (jb >> 8) & 3;
             const int nwin = (np + EPW - 1) / EPW;
             const int wstart = (warp + NWARPS - (n == 2 ? woff2 : woff1) % NWARPS) % NWARPS;
             if (n == 2) woff2 += nwin; else woff1 += nwin;
             for (int win = wstart; win < nwin; win += NWARPS) {
-                const int idx = win * EPW + k;
+                // idle lanes (beyond EPW envs, or beyond the piece's last env) mirror the lanes of the window's env 0:
+                // the same addresses as live lanes, so they add no shared-memory wavefront
+                const int idx0 = window_position<EPW, D>(win, 0, np);
+                const int idx = lane_ok ? window_position<EPW, D>(win, k, np) : idx0;
                 const bool on = lane_ok && idx < np;
-                const int env = on ? (int)sm.list[p][idx] : 0;
-                const uint32_t *rec = sm.rec + env * K::WORDS;
+                const int slot = pbase + (on ? idx : idx0);
+                const uint32_t *rec = sm.rec + slot * K::WORDS;
+                const int64_t env = e0 + (int64_t)sm.env_of[slot];
                 Neigh<C, R, W> nb;
                 load_neigh<C, R, W>(rec, c, nb);
                 uint32_t vsel = 0u, ssel = 0u;              // leader lane: legal / slow columns of its env, 16 bits per orientation
@@ -383,61 +442,68 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 for (int o = 0; o < n; ++o) {
                     const int oi = (int)((jb >> 10) & 63u) + o;
                     const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[oi]);
-                    const int slot = (int)(jb >> 16) + c * n + o;
+                    const int aslot = (int)(jb >> 16) + c * n + o;
                     bool slow = false, legal = false;
                     if (on) {
                         Eval ev;
-                        const int status = eval_neigh<C, R, W, true>(rec, sm.run, nb, u, c, ev);
-                        if (status == kFastDone) { if (slot < a_stride) emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs); }
-                        else if (status == kFastClears) slow = (!ev.terminal || want_terminal) && slot < a_stride;
-                        else slow = want_terminal && slot < a_stride;
+                        const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
+                        if (status == kFastDone) { if (aslot < a_stride) emit_row<DIRS>(feat_row(feats, env, a_stride, aslot), ev, dirs); }
+                        else if (status == kFastClears) slow = (!ev.terminal || want_terminal) && aslot < a_stride;
+                        else slow = want_terminal && aslot < a_stride;
                         legal = !ev.terminal;
                     }
                     vsel |= ((__ballot_sync(FULLMASK, legal) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
                     ssel |= ((__ballot_sync(FULLMASK, slow) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
                 }
-                if (on && c == 0) { sm.vloc[env][l] = vsel; sm.sloc[env][l] = ssel; }
+                if (on && c == 0) { sm.vloc[slot][l] = vsel; sm.sloc[slot][l] = ssel; }
             }
         };
+        {
+            int pbase = 0;
 #pragma unroll 1
-        for (int j = 0; j < kNumJobs; ++j) {
-            const uint32_t jb = sm.job[j];
-            const int np = cnt[jb & 15];
-            if (np == 0 || ((jb >> 8) & 3u) == 0u) continue;
-            switch ((jb >> 5) & 7u) {
-            case 1: column_loop(IntC<1>(), jb, np); break;
-            case 2: column_loop(IntC<2>(), jb, np); break;
-            case 3: column_loop(IntC<3>(), jb, np); break;
-            default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np); break;
+            for (int j = 0; j < kNumJobs; ++j) {
+                const uint32_t jb = sm.job[j];
+                const int np = cnt[jb & 15];
+                if (np != 0 && ((jb >> 8) & 3u) != 0u) {
+                    switch ((jb >> 5) & 7u) {
+                    case 1: column_loop(IntC<1>(), jb, np, pbase); break;
+                    case 2: column_loop(IntC<2>(), jb, np, pbase); break;
+                    case 3: column_loop(IntC<3>(), jb, np, pbase); break;
+                    default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np, pbase); break;
+                    }
+                }
+                if (j & 1) pbase += np;                    // jobs 2p, 2p + 1 = the two column loops of piece p
             }
         }
         __syncthreads();                                   // every warp is done with phase B: vloc / sloc are complete
-        // ---- phase S: the placements that need the general evaluation (they clear a line), of this warp's own 32 envs,
-        // one lane per item.  Only warp-local data from here to the next tile's phase A: no further CTA barrier
-        // (THREADS == TILE; with WPG warps per group the tile ends with a barrier instead).
+        // ---- phase S: the placements that need the general evaluation (they clear a line) of this warp's own 32 envs
+        // (of its group's, with WPG warps per group), one lane per item; nothing is written to shared memory.
         const int grp = WPG == 1 ? warp : warp % NGROUPS, sub = WPG == 1 ? 0 : warp / NGROUPS;
-        for_each_slow_item(sm.sloc[(grp << 5) + lane][0], sm.sloc[(grp << 5) + lane][1], lane, sub, WPG,
-                           [&](int owner, int l, int o, int cc) {
-            const int env = (grp << 5) + owner;
-            const uint32_t pw = sm.piece[sm.pid[env]];
+        const int gslot = WPG == 1 ? myslot : (int)sm.slot_of[(grp << 5) + lane];
+        const bool has = gslot != kNoSlot;
+        for_each_slow_item(has ? sm.sloc[gslot][0] : 0u, has ? sm.sloc[gslot][1] : 0u, gslot, lane, sub, WPG,
+                           [&](int owner, int oslot, int l, int o, int cc) {
+            const uint32_t pw = sm.piece[sm.pid[oslot]];
             const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
-            const int slot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
+            const int aslot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
             Eval ev;
-            eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
-            emit_row<DIRS>(feat_row(feats, e0 + env, a_stride, slot), ev, dirs);
+            eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
+            emit_row<DIRS>(feat_row(feats, e0 + (grp << 5) + owner, a_stride, aslot), ev, dirs);
         });
-        __syncwarp();
         // ---- legal-action masks, thread per env (coalesced)
         if (env_thread && e < sv.n_env) {
-            const uint32_t pw = sm.piece[sm.pid[tid]];
-            const int n0 = (int)(pw & 3u), n1 = (int)((pw >> 5) & 3u);
-            const int s1 = n0 * (C - (int)((pw >> 2) & 7u) + 1);
-            const unsigned long long v = (unsigned long long)slots_of(sm.vloc[tid][0], n0) |
-                                         ((unsigned long long)slots_of(sm.vloc[tid][1], n1) << s1);
+            unsigned long long v = 0ull;
+            if (myslot != kNoSlot) {
+                const uint32_t pw = sm.piece[piece];
+                const int n0 = (int)(pw & 3u), n1 = (int)((pw >> 5) & 3u);
+                const int s1 = n0 * (C - (int)((pw >> 2) & 7u) + 1);
+                v = (unsigned long long)slots_of(sm.vloc[myslot][0], n0) |
+                    ((unsigned long long)slots_of(sm.vloc[myslot][1], n1) << s1);
+            }
             if (valid_out) valid_out[e] = v;
             if (count_out) count_out[e] = __popcll(v);
         }
-        if (WPG > 1) __syncthreads();                      // the other warps of a group may still read its records / masks
+        // the next tile's phase A2 overwrites the records: it starts behind the barrier after phase A1
     }
 }
 
@@ -720,11 +786,12 @@ __device__ __forceinline__ unsigned long long score_key(uint32_t ord, int slot)
 }
 
 // Greedy linear policy.  Same tile scheme as K1; thread tid owns env tid of the tile for all n_steps.  Per step:
-// A (thread per env) env record + piece lists, B (warp per window of same-piece envs) score every legal placement and
-// keep the first arg-max per env and column loop, S (per warp) its line-clearing placements, C (thread per env) apply
-// the chosen placement.  Between steps the board lives in the record's column words, not in registers: only the
-// bag / counters stay in registers across phase B.  Episode statistics are aggregated per warp in shared memory.
-// THREADS > TILE: small-batch configuration, see afterstates_body.
+//   A (thread per env)  counting sort by piece (rank by shared atomic, barrier, slot), record built at the env's slot
+//   B (warp per window of same-piece envs)  score every legal placement, keep the first arg-max per env and column loop
+//   S (per warp, its own 32 envs)  the line-clearing placements, from scratch
+//   C (thread per env)  apply the chosen placement, next piece, game over / auto-reset; the board stays in registers
+//                       until phase A of the next step writes it into the env's NEW slot
+// Episode statistics are aggregated per warp in shared memory.  THREADS > TILE: small-batch configuration, see K1.
 template <int C, int R, int TILE, int MINB, int THREADS = TILE>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, int n_steps, F8 wts, int64_t *stats,
@@ -744,7 +811,6 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
     long long *wstat = bs.wstat[warp];
     if (lane < TB_ST_COUNT) wstat[lane] = 0;
     int par = 0;
-    uint32_t *myrec = sm.rec + (env_thread ? tid : 0) * K::WORDS;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t e = tile * TILE + tid;
@@ -752,55 +818,57 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
         bool active = in_range;                            // false once finished in a no-reset rollout
         Meta mt; mt.piece = 0; mt.bag = 0u; mt.draws = 0u;
         uint2 ep = make_uint2(0u, 0u);
-        {
-            uint32_t col[C];
-            if (in_range) {
-                load_board<C, R>(sv, e, col);
-                mt = unpack_meta(sv.meta[e]);
-                ep = sv.epi[e];
-                active = mt.piece < kNumPieces;
-            } else {
+        uint32_t col[C];                                   // the env's board between phase C and the next phase A
+        if (in_range) {
+            load_board<C, R>(sv, e, col);
+            mt = unpack_meta(sv.meta[e]);
+            ep = sv.epi[e];
+            active = mt.piece < kNumPieces;
+        } else {
 #pragma unroll
-                for (int i = 0; i < C; ++i) col[i] = 0u;
-            }
-            if (env_thread) {
-#pragma unroll
-                for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
-            }
+            for (int i = 0; i < C; ++i) col[i] = 0u;
         }
         for (int t = 0; t < n_steps; ++t, par ^= 1) {
             int *cnt = sm.cnt[par];
-            // ---- phase A (thread per env).  cnt[par] was zeroed during the previous step's phase B.
-            if (env_thread) {
-                sm.vloc[tid][0] = 0u; sm.vloc[tid][1] = 0u;
-                sm.sloc[tid][0] = 0u; sm.sloc[tid][1] = 0u;
-                bs.best[tid] = 0ull;
-            }
-            int n_slots = 0;
+            // ---- phase A1: rank among the tile's envs with the same piece.  cnt[par] was zeroed during the previous A2.
+            int rank = 0;
+            if (active) rank = atomicAdd(&cnt[mt.piece], 1);
+            __syncthreads();                               // counts complete; nobody reads the previous step's records
+            if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
+            // ---- phase A2: the record, at the env's slot
+            int myslot = kNoSlot, n_slots = 0;
             if (active) {
-                build_env<C, R>(sm.run, myrec);         // the columns are already in the record
-                sm.list[mt.piece][atomicAdd(&cnt[mt.piece], 1)] = (uint8_t)tid;
-                sm.pid[tid] = (uint8_t)mt.piece;
+                myslot = slot_from_rank(cnt, mt.piece, rank);
+                uint32_t *myrec = sm.rec + myslot * K::WORDS;
+#pragma unroll
+                for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
+                build_env<C, R>(sm.run, myrec);
+                sm.pid[myslot] = (uint8_t)mt.piece;
+                sm.vloc[myslot][0] = 0u; sm.vloc[myslot][1] = 0u;
+                sm.sloc[myslot][0] = 0u; sm.sloc[myslot][1] = 0u;
+                bs.best[myslot] = 0ull;
                 n_slots = piece_num_slots(sm.piece[mt.piece], C);
             }
+            if (WPG > 1 && env_thread) sm.slot_of[tid] = (uint16_t)myslot;
             __syncthreads();
-            if (tid <= kNumPieces) sm.cnt[par ^ 1][tid] = 0;
             // ---- phase B: score every legal placement, keep the first arg-max per env and column loop
             int woff1 = 0, woff2 = 0;                      // round robin continued across jobs, as in K1
-            auto column_loop = [&](auto wtag, uint32_t jb, int np) {
+            auto column_loop = [&](auto wtag, uint32_t jb, int np, int pbase) {
                 constexpr int W = decltype(wtag)::value;
-                constexpr int NC = C - W + 1, EPW = 32 / NC;
+                constexpr int NC = C - W + 1, EPW = 32 / NC, D = WinStride<EPW, NC, K::WORDS>::value;
                 const int k = lane / NC, c = lane - k * NC;
                 const bool lane_ok = k < EPW;
-                const int p = jb & 15, l = (jb >> 4) & 1, n = (jb >> 8) & 3;
+                const int l = (jb >> 4) & 1, n = (jb >> 8) & 3;
                 const int nwin = (np + EPW - 1) / EPW;
                 const int wstart = (warp + NWARPS - (n == 2 ? woff2 : woff1) % NWARPS) % NWARPS;
                 if (n == 2) woff2 += nwin; else woff1 += nwin;
                 for (int win = wstart; win < nwin; win += NWARPS) {
-                    const int idx = win * EPW + k;
+                    // idle lanes mirror the lanes of the window's env 0 (same addresses: no extra wavefront), see K1
+                    const int idx0 = window_position<EPW, D>(win, 0, np);
+                    const int idx = lane_ok ? window_position<EPW, D>(win, k, np) : idx0;
                     const bool on = lane_ok && idx < np;
-                    const int env = on ? (int)sm.list[p][idx] : 0;
-                    const uint32_t *rec = sm.rec + env * K::WORDS;
+                    const int slot = pbase + (on ? idx : idx0);
+                    const uint32_t *rec = sm.rec + slot * K::WORDS;
                     Neigh<C, R, W> nb;
                     load_neigh<C, R, W>(rec, c, nb);
                     uint32_t best_ord = 0u;                // this lane's best orderable score (0 = none) and its slot
@@ -810,14 +878,14 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     for (int o = 0; o < n; ++o) {
                         const int oi = (int)((jb >> 10) & 63u) + o;
                         const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[oi]);
-                        const int slot = (int)(jb >> 16) + c * n + o;
+                        const int aslot = (int)(jb >> 16) + c * n + o;
                         bool slow = false;
                         if (on) {
                             Eval ev;
-                            const int status = eval_neigh<C, R, W, true>(rec, sm.run, nb, u, c, ev);
+                            const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
                             if (status == kFastDone) {
                                 const uint32_t ord = orderable(fitness(ev.f, wts.v));         // game.py:109-120
-                                if (ord > best_ord) { best_ord = ord; best_slot = slot; }     // slots ascend with o
+                                if (ord > best_ord) { best_ord = ord; best_slot = aslot; }    // slots ascend with o
                             } else if (status == kFastClears) {
                                 slow = !ev.terminal;
                             }
@@ -835,33 +903,40 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     const uint32_t hit = (__ballot_sync(FULLMASK, best_ord == m) >> (k * NC)) & ((1u << NC) - 1u);
                     const int src = k * NC + __ffs((int)hit) - 1;              // lowest column that reaches it
                     const int sl = __shfl_sync(FULLMASK, best_slot, src & 31);
-                    if (on && c == 0) { sm.vloc[env][l] = m; bs.bslot[env][l] = (uint8_t)sl; sm.sloc[env][l] = ssel; }
+                    if (on && c == 0) { sm.vloc[slot][l] = m; bs.bslot[slot][l] = (uint8_t)sl; sm.sloc[slot][l] = ssel; }
                 }
             };
+            {
+                int pbase = 0;
 #pragma unroll 1
-            for (int j = 0; j < kNumJobs; ++j) {
-                const uint32_t jb = sm.job[j];
-                const int np = cnt[jb & 15];
-                if (np == 0 || ((jb >> 8) & 3u) == 0u) continue;
-                switch ((jb >> 5) & 7u) {
-                case 1: column_loop(IntC<1>(), jb, np); break;
-                case 2: column_loop(IntC<2>(), jb, np); break;
-                case 3: column_loop(IntC<3>(), jb, np); break;
-                default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np); break;
+                for (int j = 0; j < kNumJobs; ++j) {
+                    const uint32_t jb = sm.job[j];
+                    const int np = cnt[jb & 15];
+                    if (np != 0 && ((jb >> 8) & 3u) != 0u) {
+                        switch ((jb >> 5) & 7u) {
+                        case 1: column_loop(IntC<1>(), jb, np, pbase); break;
+                        case 2: column_loop(IntC<2>(), jb, np, pbase); break;
+                        case 3: column_loop(IntC<3>(), jb, np, pbase); break;
+                        default: column_loop(IntC<(C >= 4 ? 4 : 1)>(), jb, np, pbase); break;
+                        }
+                    }
+                    if (j & 1) pbase += np;
                 }
             }
-            __syncthreads();                               // phase B is complete: vloc / bslot / sloc of every env
-            // ---- phase S: the line-clearing legal placements of this warp's own 32 envs, one lane per item
+            __syncthreads();                               // phase B is complete: vloc / bslot / sloc of every slot
+            // ---- phase S: the line-clearing legal placements of this warp's own 32 envs, one lane per item.  Their best
+            // keys go to best[slot of the env]: only this warp (this group's warps) touches those entries.
             const int grp = WPG == 1 ? warp : warp % NGROUPS, sub = WPG == 1 ? 0 : warp / NGROUPS;
-            for_each_slow_item(sm.sloc[(grp << 5) + lane][0], sm.sloc[(grp << 5) + lane][1], lane, sub, WPG,
-                               [&](int owner, int l, int o, int cc) {
-                const int env = (grp << 5) + owner;
-                const uint32_t pw = sm.piece[sm.pid[env]];
+            const int gslot = WPG == 1 ? myslot : (int)sm.slot_of[(grp << 5) + lane];
+            const bool has = gslot != kNoSlot;
+            for_each_slow_item(has ? sm.sloc[gslot][0] : 0u, has ? sm.sloc[gslot][1] : 0u, gslot, lane, sub, WPG,
+                               [&](int owner, int oslot, int l, int o, int cc) {
+                const uint32_t pw = sm.piece[sm.pid[oslot]];
                 const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
-                const int slot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
+                const int aslot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
                 Eval ev;
-                eval_slow<C, R>(sm.rec + env * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
-                atomicMax(&bs.best[env], score_key(orderable(fitness(ev.f, wts.v)), slot));
+                eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
+                atomicMax(&bs.best[oslot], score_key(orderable(fitness(ev.f, wts.v)), aslot));
             });
             if (WPG == 1) __syncwarp();                    // phase C reads the best keys of this warp's envs only
             else __syncthreads();                          // ... or of a group that several warps worked on
@@ -870,24 +945,25 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             bool placed = false, dn = false;
             uint2 ep_done = make_uint2(0u, 0u);
             if (active) {
-                uint32_t col[C];
+                // the board comes back from the record (not kept in registers across phase B)
+                const uint32_t *myrec = sm.rec + myslot * K::WORDS;
 #pragma unroll
                 for (int i = 0; i < C; ++i) col[i] = myrec[K::COLX + 2 + i];
                 const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
-                unsigned long long best = bs.best[tid];
+                unsigned long long best = bs.best[myslot];
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
-                    const uint32_t m = sm.vloc[tid][l];
+                    const uint32_t m = sm.vloc[myslot][l];
                     if (m != 0u) {
-                        const unsigned long long k64 = score_key(m, (int)bs.bslot[tid][l]);
+                        const unsigned long long k64 = score_key(m, (int)bs.bslot[myslot][l]);
                         best = k64 > best ? k64 : best;
                     }
                 }
                 if (best != 0ull) {
-                    const int slot = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
+                    const int aslot = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
                     int ori, cc, a, term;
                     uint32_t full;
-                    slot_to_placement(sm.piece[mt.piece], C, slot, ori, cc);
+                    slot_to_placement(sm.piece[mt.piece], C, aslot, ori, cc);
                     place_and_clear<C, R>(col, sm.ori[ori], cc, a, full, term);
                     lc = popc32(full);
                     placed = true;
@@ -906,8 +982,6 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     mt.piece = set_piece(piece_set, bag_draw(set_size(piece_set), key, mt.bag, mt.draws));
                     ep = make_uint2(0u, 0u);
                 }
-#pragma unroll
-                for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
             }
             // episode statistics of the step, aggregated over the warp (ballots are warp-uniform; lane 0 accumulates)
             {
@@ -935,11 +1009,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 }
             }
         }
-        __syncthreads();                                   // nobody reads this thread's record any more
         if (in_range && (active || mt.piece == kPieceDead)) {
-            uint32_t col[C];
-#pragma unroll
-            for (int i = 0; i < C; ++i) col[i] = myrec[K::COLX + 2 + i];
             store_board<C, R>(sv, e, col);
             sv.meta[e] = pack_meta<C>(col, mt);
             sv.epi[e] = ep;
@@ -1151,8 +1221,8 @@ static inline unsigned grid_for(const TbLaunchCtx *cx, int64_t work_items, int p
 // Tile configuration by batch size: the throughput configuration (cfg 0, 256-env tiles, thread per env) once there is
 // at least one tile per SM; below that 128-env tiles (`mid`); and for batches of at most cx->small_groups (default 4)
 // 32-env groups per SM the small-batch configuration 4 (32 envs and 4 warps per CTA: shortest critical path).
-//   K1 cfg  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5
-//   K3 cfg  0: 256 x 2 (default)   2: 128 x 4   3: 128 x 5
+//   K1 cfg  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5   6: 256 x 4
+//   K3 cfg  0: 256 x 3, 80 registers (default)   2: 128 x 4   3: 128 x 5   7: 256 x 2, 125 registers
 //   both    4: 32 envs x 128 threads   5: 64 envs x 256 threads   (several warps per 32-env group, small batches)
 static inline int small_batch_cfg(const TbLaunchCtx *cx, int64_t n_env, int mid)
 {
@@ -1195,6 +1265,8 @@ struct ShapeOps {
             kern = directions ? k_afterstates<C, R, true, 128, 5> : k_afterstates<C, R, false, 128, 5>; }
         else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<C, R, 256>);
             kern = directions ? k_afterstates<C, R, true, 256, 2> : k_afterstates<C, R, false, 256, 2>; }
+        else if (cfg == 6) { tile = 256; minb = 4; smem = sizeof(CtaSmem<C, R, 256>);
+            kern = directions ? k_afterstates<C, R, true, 256, 4> : k_afterstates<C, R, false, 256, 4>; }
         else { tile = 256; minb = 3; smem = sizeof(CtaSmem<C, R, 256>);
             kern = directions ? k_afterstates<C, R, true, 256, 3> : k_afterstates<C, R, false, 256, 3>; }
         if (opt_in_smem(cx, (const void *)kern, smem)) return -2;
@@ -1243,7 +1315,10 @@ struct ShapeOps {
             smem = ((sizeof(CtaSmem<C, R, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }
         else if (cfg == 2) { tile = 128; minb = 4; kern = k_rollout_greedy<C, R, 128, 4>;
             smem = ((sizeof(CtaSmem<C, R, 128>) + 15) & ~(size_t)15) + sizeof(BestSmem<128>); }
-        else { tile = 256; minb = 2; kern = k_rollout_greedy<C, R, 256, 2>;
+        else if (cfg == 7) { tile = 256; minb = 2; kern = k_rollout_greedy<C, R, 256, 2>;
+            smem = ((sizeof(CtaSmem<C, R, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }
+        else { tile = 256; minb = 3; kern = k_rollout_greedy<C, R, 256, 3>;   /* 80 registers: the spills sit at the phase
+            boundaries (once per env and step), none in phase B; 3 CTAs per SM beat 2 at 125 registers by 5 % */
             smem = ((sizeof(CtaSmem<C, R, 256>) + 15) & ~(size_t)15) + sizeof(BestSmem<256>); }
         if (opt_in_smem(cx, (const void *)kern, smem)) return -2;
         kern<<<grid_for(cx, n_env, tile, minb, 16), threads ? threads : tile, smem, st>>>(
