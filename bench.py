@@ -420,26 +420,32 @@ def run_ours(args):
             nl = min(E, 1 << 18)
             env2 = BatchedTetris(C, R, nl, piece_set=PIECE_SET, seed=args.seed + 1, device=dev)
             env2.rollout(20, "random")
-            hf = torch.empty((nl, env2.a_max, 8), dtype=torch.float32).pin_memory()
             hc = torch.empty(nl, dtype=torch.int32).pin_memory()
             ha = torch.zeros(nl, dtype=torch.int32).pin_memory()
             ho = torch.empty((nl, 8), dtype=torch.float32).pin_memory()
             n_it = 3
-            for it in range(n_it + 1):                                 # first iteration = warm-up (pinned pages, caches)
-                if it == 1:
+            for compact in (False, True):                              # float32 rows, then the int16 (2 x feature) rows
+                hf = torch.empty((nl, env2.a_max, 8), dtype=torch.int16 if compact else torch.float32).pin_memory()
+                df = torch.empty((nl, env2.a_max, 8), dtype=hf.dtype, device=dev)
+                dv = torch.empty(nl, dtype=torch.int64, device=dev)
+                dc = torch.empty(nl, dtype=torch.int32, device=dev)
+                for it in range(n_it + 1):                             # first iteration = warm-up (pinned pages, caches)
+                    if it == 1:
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                    f, v, c = env2.get_after_states(out=(df, dv, dc), compact=compact)
+                    hf.copy_(f, non_blocking=True); hc.copy_(c, non_blocking=True)
                     torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                f, v, c = env2.get_after_states()
-                hf.copy_(f, non_blocking=True); hc.copy_(c, non_blocking=True)
-                torch.cuda.synchronize()
-                obs, rew, done, lines = env2.step(ha.to(dev, non_blocking=True), auto_reset=True, check=False)
-                ho.copy_(obs, non_blocking=True)
-                torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            out["e2e_lockstep_host_policy"] = {
-                "value": nl * n_it / dt, "unit": "placements/s", "envs": nl,
-                "h2d_bytes_per_step": 4 * nl, "d2h_bytes_per_step": nl * (env2.a_max * 32 + 4 + 32),
-                "note": "get_after_states -> features D2H -> actions H2D -> step -> obs D2H (action 0 for all envs)"}
+                    obs, rew, done, lines = env2.step(ha.to(dev, non_blocking=True), auto_reset=True, check=False)
+                    ho.copy_(obs, non_blocking=True)
+                    torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                out["e2e_lockstep_host_policy" + ("_compact" if compact else "")] = {
+                    "value": nl * n_it / dt, "unit": "placements/s", "envs": nl,
+                    "h2d_bytes_per_step": 4 * nl, "d2h_bytes_per_step": nl * (env2.a_max * (16 if compact else 32) + 4 + 32),
+                    "note": "get_after_states -> features D2H -> actions H2D -> step -> obs D2H (action 0 for all envs)"
+                            + ("; features as int16 = 2 x feature (TB_FLAG_FEATS_I16)" if compact else "")}
+                del hf, df
             del env2
         except Exception as ex:                                        # side measurement only
             out["e2e_lockstep_host_policy"] = {"error": repr(ex)}

@@ -57,6 +57,9 @@ extern "C" {
                                       (get_after_states(include_terminal=True), game.py:74-78)               */
 #define TB_FLAG_VALIDATE_ONLY  8   /* step: dry run -- only status_out is produced, no env is touched; lets a caller
                                       raise the reference's IndexError (game.py:83) BEFORE any env is stepped  */
+#define TB_FLAG_FEATS_I16      16  /* afterstates: feats_out is int16[n_env][a_stride][8] holding 2 x feature
+                                      (x direction): every feature is a half-integer below 2^14, so this is exact
+                                      at half the bytes -- for policies on the host (PCIe) or bandwidth-bound readers */
 
 /* tb_rollout policies */
 #define TB_POLICY_RANDOM 0         /* uniformly random legal placement (per-env counter RNG, stream 1)       */
@@ -127,7 +130,7 @@ int tb_reset(void *state, int num_columns, int num_rows, int64_t n_env, int64_t 
  *   valid_out   nullable uint64[n_env]: bit s set  <=>  slot s is a non-terminal afterstate (a legal action)
  *   count_out   nullable int32[n_env]: number of legal actions (len(self.afterstates), game.py:69)
  *   directions  nullable HOST float[8]: per-feature multipliers (feature_directions, state.py:49-50), applied in fp32
- *   flags       0 or TB_FLAG_INCLUDE_TERMINAL
+ *   flags       TB_FLAG_INCLUDE_TERMINAL, TB_FLAG_FEATS_I16 (feats_out then is int16[n_env][a_stride][8] = 2 x feature)
  */
 int tb_afterstates(const void *state, int num_columns, int num_rows, int64_t n_env, void *feats_out,
                    uint64_t *valid_out, int32_t *count_out, int a_stride, const float *directions, int flags,

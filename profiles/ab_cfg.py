@@ -16,6 +16,8 @@ from tetris_b200 import BatchedTetris, _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--k1", default="0,6,2")
 ap.add_argument("--k3", default="0,6")
+ap.add_argument("--k2", default="0")
+ap.add_argument("--k3r", default="0")
 ap.add_argument("--envs", type=int, default=1 << 20)
 ap.add_argument("--board", default="10x20")
 a = ap.parse_args()
@@ -52,6 +54,13 @@ for cfg in [int(x) for x in a.k1.split(",") if x != ""]:
     out["k1_cfg%d_ms" % cfg] = ms
     out["k1_cfg%d_checksum" % cfg] = int(count.sum().item())
 _lib.set_tuning("k1_cfg", -1)
+try:                                            # compact int16 output (TB_FLAG_FEATS_I16), default configuration
+    feats16 = torch.empty((n, env.a_max, 8), dtype=torch.int16, device="cuda")
+    for _ in range(3):
+        env.get_after_states(out=(feats16, valid, count), compact=True)
+    out["k1_i16_ms"] = timed(lambda: env.get_after_states(out=(feats16, valid, count), compact=True), 9)
+except TypeError:
+    pass
 for cfg in [int(x) for x in a.k3.split(",") if x != ""]:
     _lib.set_tuning("k3_cfg", cfg)
     env.state.copy_(saved)
@@ -60,13 +69,34 @@ for cfg in [int(x) for x in a.k3.split(",") if x != ""]:
     out["k3_cfg%d_ms_per_32" % cfg] = ms
     out["k3_cfg%d_placements_per_s" % cfg] = n * 32 / (ms * 1e-3)
 _lib.set_tuning("k3_cfg", -1)
-env.state.copy_(saved)
+def tune(name, v):
+    try:
+        _lib.set_tuning(name, v)
+        return True
+    except Exception:                       # older library in an A/B run: no such knob
+        return False
+
+
 a0 = torch.zeros(n, dtype=torch.int32, device="cuda")
-for _ in range(2):
-    env.step(a0, auto_reset=True, check=False)
-env.state.copy_(saved)
-out["k2_ms"] = timed(lambda: env.step(a0, auto_reset=True, check=False), 5)
 envr = BatchedTetris(C, R, n, piece_set=1, seed=7)
 envr.rollout(30, "random")
-out["k3r_ms_per_32"] = timed(lambda: envr.rollout(32, "random"), 5)
+saved_r = envr.state.clone()
+for cfg in [int(x) for x in a.k2.split(",") if x != ""]:
+    if not tune("k2_cfg", cfg) and cfg != 0:
+        continue
+    env.state.copy_(saved)
+    for _ in range(2):
+        env.step(a0, auto_reset=True, check=False)
+    env.state.copy_(saved)
+    out["k2_cfg%d_ms" % cfg] = timed(lambda: env.step(a0, auto_reset=True, check=False), 5)
+    envr.state.copy_(saved_r)                # tall boards (random play): many envs need the legality test
+    out["k2_cfg%d_tall_ms" % cfg] = timed(lambda: envr.step(a0, auto_reset=True, check=False), 5)
+tune("k2_cfg", -1)
+for cfg in [int(x) for x in a.k3r.split(",") if x != ""]:
+    if not tune("k3r_cfg", cfg) and cfg != 0:
+        continue
+    envr.state.copy_(saved_r)
+    envr.rollout(32, "random")
+    out["k3r_cfg%d_ms_per_32" % cfg] = timed(lambda: envr.rollout(32, "random"), 5)
+tune("k3r_cfg", -1)
 print(json.dumps(out))

@@ -687,3 +687,26 @@ def test_rollouts_fixture():
         ret, bits = replay_rollout_config(c, _CudaRolloutBatch)
         assert np.array_equal(bits, c["valid"]), (c["C"], c["R"], c["policy"])
         assert np.array_equal(ret, c["ret_sum"]), (c["C"], c["R"], c["policy"])
+
+
+def test_compact_features():
+    """TB_FLAG_FEATS_I16: the int16 output is exactly 2 x the float32 features (x directions), for legal rows and --
+    with include_terminal -- for terminal rows; masks and counts are unchanged.  Small and headline boards."""
+    torch = _torch()
+    from tetris_b200 import BatchedTetris, _lib
+    for (Cc, R, n) in ((10, 20, 5000), (6, 12, 1500)):
+        env = BatchedTetris(Cc, R, n, piece_set=1, seed=5)
+        env.rollout(25, "random")
+        n_all = torch.as_tensor([_lib.lib().tb_num_slots(p, Cc) for p in range(9)], device="cuda")[env.export_boards()[2].long()]
+        slot = torch.arange(env.a_max, device="cuda")[None, :]
+        for dirs in (None, [-1, -1, -1, -1, -1, -1, 1, -1]):
+            env.set_directions(dirs)
+            for term in (False, True):
+                f, v, c = env.get_after_states(include_terminal=term)
+                h, v2, c2 = env.get_after_states(include_terminal=term, compact=True)
+                assert h.dtype == torch.int16 and h.shape == f.shape
+                assert torch.equal(v, v2) and torch.equal(c, c2)
+                mask = (slot < n_all[:, None]) if term else ((v[:, None] >> slot) & 1).bool()
+                assert torch.equal(h[mask].float() * 0.5, f[mask]), (Cc, R, dirs, term)
+                assert int(mask.sum()) > 5 * n
+        env.set_directions(None)

@@ -24,6 +24,7 @@ FLAG_AUTO_RESET = 1
 FLAG_ACTION_IS_SLOT = 2
 FLAG_INCLUDE_TERMINAL = 4
 FLAG_VALIDATE_ONLY = 8
+FLAG_FEATS_I16 = 16
 POLICY_RANDOM = 0
 POLICY_GREEDY = 1
 STATS = ("placements", "episodes", "lines", "reward", "afterstates",

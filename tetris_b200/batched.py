@@ -101,26 +101,30 @@ class BatchedTetris:
             _lib.check(_lib.lib().tb_reset(*self._common(), self.env_offset, self.seed, self.piece_set,
                                            _ptr(t), _ptr(m), self._stream()))
 
-    def get_after_states(self, include_terminal=False, out=None):
+    def get_after_states(self, include_terminal=False, out=None, compact=False):
         """Tetris.get_after_states for every env (game.py:67-80).
 
         Returns (features float32[n_env, a_max, 8] by enumeration slot, valid int64[n_env] bit mask of
         non-terminal slots, count int32[n_env]).  Legal action k of env e is the k-th set bit of valid[e].
         Feature rows of terminal afterstates are written only with include_terminal=True (game.py:74-78);
         rows past the piece's slot count are never written.
+        compact=True: features come as int16[n_env, a_max, 8] holding 2 x feature (every feature is a half-integer,
+        so this is exact): half the bytes for a policy that reads them on the host; `features * 0.5` restores them.
         """
         if out is None:
-            feats = torch.empty((self.n_env, self.a_max, 8), dtype=torch.float32, device=self.device)
+            feats = torch.empty((self.n_env, self.a_max, 8), dtype=torch.int16 if compact else torch.float32,
+                                device=self.device)
             valid = torch.empty(self.n_env, dtype=torch.int64, device=self.device)
             count = torch.empty(self.n_env, dtype=torch.int32, device=self.device)
         else:
             feats, valid, count = out
+            if feats.dtype != (torch.int16 if compact else torch.float32):
+                raise ValueError("out[0] must be %s" % ("int16 with compact=True" if compact else "float32"))
         d = None if self._dirs is None else self._dirs.ctypes.data_as(C.c_void_p)
+        flags = (_lib.FLAG_INCLUDE_TERMINAL if include_terminal else 0) | (_lib.FLAG_FEATS_I16 if compact else 0)
         with self._on_device():
             _lib.check(_lib.lib().tb_afterstates(*self._common(), _ptr(feats), _ptr(valid), _ptr(count),
-                                                 self.a_max, d,
-                                                 _lib.FLAG_INCLUDE_TERMINAL if include_terminal else 0,
-                                                 self._stream()))
+                                                 self.a_max, d, flags, self._stream()))
         return feats, valid, count
 
     def step(self, actions, tape=None, auto_reset=False, action_is_slot=False, check=True):

@@ -201,10 +201,10 @@ static int sm_count()
 
 // Tuning knobs (experiments and tests only; the defaults are what ships).  Read from the environment ONCE, when the
 // first launch needs them (TB_K1_CFG, TB_K3_CFG, TB_SMALL_GROUPS, TB_MAX_CTAS), and settable through tb_set_tuning().
-enum { TUNE_K1_CFG = 0, TUNE_K3_CFG, TUNE_SMALL_GROUPS, TUNE_MAX_CTAS, TUNE_COUNT };
-static const char *const kTuneNames[TUNE_COUNT] = {"k1_cfg", "k3_cfg", "small_groups", "max_ctas"};
-static const char *const kTuneEnv[TUNE_COUNT] = {"TB_K1_CFG", "TB_K3_CFG", "TB_SMALL_GROUPS", "TB_MAX_CTAS"};
-static const int kTuneDefault[TUNE_COUNT] = {-1, -1, 4, 0};
+enum { TUNE_K1_CFG = 0, TUNE_K3_CFG, TUNE_SMALL_GROUPS, TUNE_MAX_CTAS, TUNE_K2_CFG, TUNE_K3R_CFG, TUNE_COUNT };
+static const char *const kTuneNames[TUNE_COUNT] = {"k1_cfg", "k3_cfg", "small_groups", "max_ctas", "k2_cfg", "k3r_cfg"};
+static const char *const kTuneEnv[TUNE_COUNT] = {"TB_K1_CFG", "TB_K3_CFG", "TB_SMALL_GROUPS", "TB_MAX_CTAS", "TB_K2_CFG", "TB_K3R_CFG"};
+static const int kTuneDefault[TUNE_COUNT] = {-1, -1, 4, 0, -1, -1};
 static std::atomic<int> g_tune[TUNE_COUNT];
 static void init_tuning()
 {
@@ -224,6 +224,8 @@ static TbLaunchCtx make_ctx(void *stream)
     cx.sm_count = sm_count();
     cx.k1_cfg = g_tune[TUNE_K1_CFG].load(std::memory_order_relaxed);
     cx.k3_cfg = g_tune[TUNE_K3_CFG].load(std::memory_order_relaxed);
+    cx.k2_cfg = g_tune[TUNE_K2_CFG].load(std::memory_order_relaxed);
+    cx.k3r_cfg = g_tune[TUNE_K3R_CFG].load(std::memory_order_relaxed);
     cx.small_groups = g_tune[TUNE_SMALL_GROUPS].load(std::memory_order_relaxed);
     cx.max_ctas = g_tune[TUNE_MAX_CTAS].load(std::memory_order_relaxed);
     cx.err = g_err;

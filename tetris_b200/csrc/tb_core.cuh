@@ -439,14 +439,19 @@ TB_HD int place_and_clear(uint32_t *col, uint32_t d, int c, int &a_out, uint32_t
 // Slow (general) path: build the afterstate board, clear, evaluate from scratch.
 // `col` is the current board (not modified unless out_col == col); out_col (nullable) gets the afterstate.
 template <int C, int R>
-TB_HD void eval_slow(const uint32_t *col, uint32_t d, int c, Eval &e, uint32_t *out_col)
+TB_HD void eval_full_tab(const uint32_t *col, const uint32_t *runtab, int *out6);   // below, after the run-sum table
+
+// runtab (nullable): the run-sum table; with it the afterstate must be NON-TERMINAL (eval_full_tab).
+template <int C, int R>
+TB_HD void eval_slow(const uint32_t *col, uint32_t d, int c, Eval &e, uint32_t *out_col, const uint32_t *runtab = nullptr)
 {
     uint32_t nc[C];
 #pragma unroll
     for (int k = 0; k < C; ++k) nc[k] = col[k];
     const int cells = place_and_clear<C, R>(nc, d, c, e.a, e.full, e.terminal);
     int six[6];
-    eval_full<C, R>(nc, six);
+    if (runtab) eval_full_tab<C, R>(nc, runtab, six);
+    else eval_full<C, R>(nc, six);
     const int ncl = popc32(e.full);
     e.f[0] = (float)six[0]; e.f[1] = (float)six[1]; e.f[2] = (float)six[2];
     e.f[3] = (float)(2 * (e.a + 1) + desc_bonus2(d)) * 0.5f;      // state.py:102 (pre-clear anchor)
@@ -515,6 +520,40 @@ TB_HD uint32_t run_sum_acc(const uint32_t *tab, uint32_t w, uint32_t acc)
 }
 template <int R>
 TB_HD int run_sum_tab(const uint32_t *tab, uint32_t w) { return (int)run_sum_acc<R>(tab, w, 0u); }
+
+// eval_full for NON-TERMINAL boards (every column height <= R: well masks stay below row R), cumulative wells by table:
+// no data-dependent POPC loop, so the lanes of a warp stay together.  Same out6 as eval_full.
+template <int C, int R>
+TB_HD void eval_full_tab(const uint32_t *col, const uint32_t *runtab, int *out6)
+{
+    using S = Shape<C, R>;
+    int holes = 0, ct = 0, hd = 0, rt = 0;
+    uint32_t wells = 0u, hm = 0u, L = S::ALL;
+    int hL = R;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const uint32_t x = col[c];
+        const int h = height_of(x);
+        const uint32_t Rt = (c + 1 < C) ? col[c + 1] : S::ALL;
+        const uint32_t mh = mask_lo(h);
+        const uint32_t hole = ~x & mh;
+        holes += popc32(hole);                                   // state.py:213
+        hm |= hole;                                              // :215
+        uint32_t t = hole & (x >> 1);                            // top cell of every vertical hole run
+        ct += 1 + 2 * popc32(t);                                 // :194,:219-220,:242-243
+        while (t) {                                              // :216 filled cells above the run
+            const int r = ctz32(t);
+            hd += popc32(x >> (r + 1));
+            t &= t - 1;
+        }
+        wells = run_sum_acc<R>(runtab, L & Rt & ~x, wells);      // :222-233,:262-272 (heights <= R: no limit mask needed)
+        if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh); // :203-204,:225-226,:246-248
+        else rt += popc32(L & mask_lo(hL));                      // :254
+        L = x; hL = h;
+    }
+    rt += R - popc32(col[C - 1]);                                // :190 right wall
+    out6[0] = popc32(hm); out6[1] = ct; out6[2] = holes; out6[3] = (int)wells; out6[4] = rt; out6[5] = hd;
+}
 
 // Small non-negative int -> float without the conversion unit: the bit pattern 0x4B000000 + v is the float
 // 2^23 + v.  The env record keeps its totals already biased, so adding a placement's integer delta yields the

@@ -210,6 +210,8 @@ struct CtaSmem {
                                          // per column loop, same bit layout as vloc in K1 (16 bits per orientation)
     alignas(16) uint32_t run[RunTab<R>::SIZE];
     uint16_t slot_of[TILE];              // env (thread of the tile) -> slot; kNoSlot: the env takes no part
+    uint16_t sprefix[TILE];              // K1 phase S: inclusive count of slow items over the slots of each 32-slot group
+    int wtot[TILE / 32];                 //             and the groups' totals
     uint8_t env_of[TILE];                // slot -> env (thread of the tile)
     uint8_t pid[TILE];                   // by slot: piece
     int cnt[2][kNumPieces + 1];          // envs per piece, double-buffered by tile / step parity
@@ -335,11 +337,30 @@ __device__ __forceinline__ uint32_t slots_of(uint32_t v, int n)
     return n == 2 ? (spread16(v & 0xFFFFu) | (spread16(v >> 16) << 1)) : (v & 0xFFFFu);
 }
 
-template <bool DIRS>
+// Output formats of K1 (template parameter FMT):
+//   0  float32[8] per afterstate (32 B)                       1  float32[8] x feature_directions (state.py:49-50)
+//   2  int16[8] = 2 x feature x direction (16 B, TB_FLAG_FEATS_I16): every feature is a half-integer below 2^14, so the
+//      doubled value is an exact small integer -- half the bytes over HBM and PCIe for a host-side policy
+constexpr int kFmtF32 = 0, kFmtF32Dirs = 1, kFmtI16 = 2;
+// int16 pair (2 f0 d0, 2 f1 d1) without the conversion unit: 2 f d + 1.5 * 2^23 is exact (a small integer), and the
+// float's low 16 mantissa bits then ARE the two's-complement int16; one FFMA per value and one PRMT per pair.
+__device__ __forceinline__ uint32_t pack_i16x2(float f0, float d0, float f1, float d1)
+{
+    const uint32_t a = __float_as_uint(__fmaf_rn(f0, d0 + d0, 12582912.0f));
+    const uint32_t b = __float_as_uint(__fmaf_rn(f1, d1 + d1, 12582912.0f));
+    return __byte_perm(a, b, 0x5410);
+}
+template <int FMT>
 __device__ __forceinline__ void emit_row(float *__restrict__ row, const Eval &ev, const F8 &dirs)
 {
+    if (FMT == kFmtI16) {
+        *reinterpret_cast<uint4 *>(row) = make_uint4(
+            pack_i16x2(ev.f[0], dirs.v[0], ev.f[1], dirs.v[1]), pack_i16x2(ev.f[2], dirs.v[2], ev.f[3], dirs.v[3]),
+            pack_i16x2(ev.f[4], dirs.v[4], ev.f[5], dirs.v[5]), pack_i16x2(ev.f[6], dirs.v[6], ev.f[7], dirs.v[7]));
+        return;
+    }
     float4 *dst = reinterpret_cast<float4 *>(row);
-    if (DIRS) {
+    if (FMT == kFmtF32Dirs) {
         dst[0] = make_float4(ev.f[0] * dirs.v[0], ev.f[1] * dirs.v[1], ev.f[2] * dirs.v[2], ev.f[3] * dirs.v[3]);
         dst[1] = make_float4(ev.f[4] * dirs.v[4], ev.f[5] * dirs.v[5], ev.f[6] * dirs.v[6], ev.f[7] * dirs.v[7]);
     } else {
@@ -347,9 +368,11 @@ __device__ __forceinline__ void emit_row(float *__restrict__ row, const Eval &ev
         dst[1] = make_float4(ev.f[4], ev.f[5], ev.f[6], ev.f[7]);
     }
 }
+// row of afterstate `slot` of env: 8 floats, or 8 int16 (= 4 floats' worth of bytes) in the compact format
+template <int FMT>
 __device__ __forceinline__ float *feat_row(float *__restrict__ feats, int64_t env, int a_stride, int slot)
 {
-    return feats + ((size_t)env * (size_t)a_stride + (size_t)slot) * 8;
+    return feats + ((size_t)env * (size_t)a_stride + (size_t)slot) * (FMT == kFmtI16 ? 4 : 8);
 }
 
 template <int V> struct IntC { static constexpr int value = V; };
@@ -367,7 +390,7 @@ __device__ __forceinline__ int slot_from_rank(const int *cnt, int piece, int ran
 // per-env phases).  THREADS > TILE is the small-batch configuration: the per-env phases use the first TILE threads,
 // phase B spreads the windows over all warps and WPG = THREADS / TILE warps share the phase-S items of each 32-env
 // group, which shortens the critical path of a tile when there are fewer tiles than SMs.
-template <int C, int R, bool DIRS, int TILE, int THREADS>
+template <int C, int R, int FMT, int TILE, int THREADS>
 __device__ __forceinline__ void
 afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
                  int *__restrict__ count_out, int a_stride, const F8 &dirs, int flags)
@@ -447,7 +470,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                     if (on) {
                         Eval ev;
                         const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
-                        if (status == kFastDone) { if (aslot < a_stride) emit_row<DIRS>(feat_row(feats, env, a_stride, aslot), ev, dirs); }
+                        if (status == kFastDone) { if (aslot < a_stride) emit_row<FMT>(feat_row<FMT>(feats, env, a_stride, aslot), ev, dirs); }
                         else if (status == kFastClears) slow = (!ev.terminal || want_terminal) && aslot < a_stride;
                         else slow = want_terminal && aslot < a_stride;
                         legal = !ev.terminal;
@@ -476,20 +499,59 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             }
         }
         __syncthreads();                                   // every warp is done with phase B: vloc / sloc are complete
-        // ---- phase S: the placements that need the general evaluation (they clear a line) of this warp's own 32 envs
-        // (of its group's, with WPG warps per group), one lane per item; nothing is written to shared memory.
-        const int grp = WPG == 1 ? warp : warp % NGROUPS, sub = WPG == 1 ? 0 : warp / NGROUPS;
-        const int gslot = WPG == 1 ? myslot : (int)sm.slot_of[(grp << 5) + lane];
-        const bool has = gslot != kNoSlot;
-        for_each_slow_item(has ? sm.sloc[gslot][0] : 0u, has ? sm.sloc[gslot][1] : 0u, gslot, lane, sub, WPG,
-                           [&](int owner, int oslot, int l, int o, int cc) {
-            const uint32_t pw = sm.piece[sm.pid[oslot]];
-            const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
-            const int aslot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
-            Eval ev;
-            eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
-            emit_row<DIRS>(feat_row(feats, e0 + (grp << 5) + owner, a_stride, aslot), ev, dirs);
-        });
+        // ---- phase S: the placements that need the general evaluation (they clear a line), pooled over the CTA: thread t
+        // counts the items of SLOT t, an inclusive scan per warp + the warps' totals give every item a global index, and
+        // the items are dealt to all lanes of all warps 32 at a time -- full warps however the items are spread over the
+        // slots (round 1 flattened them per warp: 13 of 32 lanes active, a fifth of K1's stall samples).
+        {
+            int n_active = 0;
+#pragma unroll
+            for (int q = 0; q < kNumPieces; ++q) n_active += cnt[q];
+            uint32_t m0 = 0u, m1 = 0u;
+            if (env_thread && tid < n_active) { m0 = sm.sloc[tid][0]; m1 = sm.sloc[tid][1]; }
+            int incl = __popc(m0) + __popc(m1);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULLMASK, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (env_thread) {
+                sm.sprefix[tid] = (uint16_t)incl;
+                if (lane == 31) sm.wtot[warp] = incl;
+            }
+            __syncthreads();
+            int goff[NGROUPS + 1];
+            goff[0] = 0;
+#pragma unroll
+            for (int g = 0; g < NGROUPS; ++g) goff[g + 1] = goff[g] + sm.wtot[g];
+            const int total = goff[NGROUPS];
+            for (int i = tid; i < total; i += THREADS) {
+                int g = 0;
+#pragma unroll
+                for (int q = 1; q < NGROUPS; ++q) g += goff[q] <= i;
+                const int li = i - goff[g];
+                const uint16_t *pre = sm.sprefix + (g << 5);
+                int owner = 0;                             // first slot of the group whose inclusive prefix exceeds li
+#pragma unroll
+                for (int step = 16; step; step >>= 1)
+                    if ((int)pre[owner + step - 1] <= li) owner += step;
+                const int oslot = (g << 5) + owner;
+                const uint32_t om0 = sm.sloc[oslot][0], om1 = sm.sloc[oslot][1];
+                const int r = li - ((int)pre[owner] - __popc(om0) - __popc(om1)), p0 = __popc(om0);
+                const int l = r >= p0;
+                const int bit = (int)__fns(l ? om1 : om0, 0u, (l ? r - p0 : r) + 1);
+                const int o = bit >> 4, cc = bit & 15;
+                const uint32_t pw = sm.piece[sm.pid[oslot]];
+                const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
+                const int aslot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
+                Eval ev;
+                // terminal afterstates (only evaluated with TB_FLAG_INCLUDE_TERMINAL) need the general wells code; without
+                // the flag every item is a legal placement and the table form applies (kernel-uniform choice)
+                eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr,
+                                want_terminal ? nullptr : sm.run);
+                emit_row<FMT>(feat_row<FMT>(feats, e0 + (int64_t)sm.env_of[oslot], a_stride, aslot), ev, dirs);
+            }
+        }
         // ---- legal-action masks, thread per env (coalesced)
         if (env_thread && e < sv.n_env) {
             unsigned long long v = 0ull;
@@ -507,12 +569,12 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     }
 }
 
-template <int C, int R, bool DIRS, int TILE, int MINB, int THREADS = TILE>
+template <int C, int R, int FMT, int TILE, int MINB, int THREADS = TILE>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_afterstates(StateView sv, float *__restrict__ feats, unsigned long long *__restrict__ valid_out,
               int *__restrict__ count_out, int a_stride, F8 dirs, int flags)
 {
-    afterstates_body<C, R, DIRS, TILE, THREADS>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
+    afterstates_body<C, R, FMT, TILE, THREADS>(sv, feats, valid_out, count_out, a_stride, dirs, flags);
 }
 // Afterstates with boards (compat layer / small batches): one thread per (env, slot), general path.
 template <int C, int R>
@@ -558,76 +620,143 @@ k_afterstates_export(StateView sv, float *__restrict__ feats, uint16_t *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2 step
+// K2 step.
+//
+// A CTA owns a tile of TILE envs, thread per env, in two passes of the same shape:
+//   pass 0  load + transpose the board; envs whose stack is within 4 rows of the top ("tall": a placement may be
+//           terminal) are appended to a list, their columns staged in shared memory
+//   pooled  the legality masks of the CTA's tall envs, one thread per LISTED env: the warps that hold list entries run
+//           the column-parallel legality test with full lanes instead of every warp running it for its 2-3 tall lanes
+//           (round 1: 39 % of K2's warp-instructions ran with 3 of 32 lanes), the others wait at the barrier
+//   pass 1  rank-select the action among the legal slots (game.py:83), place + clear, the chosen afterstate's features
+//           from scratch (cumulative wells by table: no data-dependent POPC loop), next piece; envs that are tall NOW
+//           are listed again
+//   pooled  same code (one copy: the pass loop is rolled), now deciding game over (game.py:94-100)
+//   finish  reward / done, auto-reset, stores.
+// On a low board every slot is legal and neither pooled phase has work for the env.
 // ---------------------------------------------------------------------------------------------
-// 8 CTAs per SM (64 registers, 16 bytes of spill): thread-per-env code is latency-bound and wants warps more than
-// registers -- 0.182 -> 0.155 ms per 2^20 envs against 5 CTAs at 96 registers; 10 / 12 CTAs (48 / 40 registers) lose again
-template <int C, int R>
-__global__ void __launch_bounds__(128, 8)
+template <int C, int R, int TILE>
+struct StepSmem {
+    uint32_t cols[TILE][C | 1];          // columns of the listed envs (odd stride)
+    alignas(16) uint32_t run[RunTab<R>::SIZE];
+    unsigned long long vmask[TILE];      // by env: legal slots, written by the pooled phase
+    uint16_t list[TILE];                 // listed (tall) envs of the current pass
+    uint8_t lpiece[TILE];                // by env: piece to test in the pooled phase
+    int n_list[2];
+    uint32_t ori[32], piece[16];
+};
+
+template <int C, int R, int TILE, int MINB>
+__global__ void __launch_bounds__(TILE, MINB)
 k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int32_t *__restrict__ actions,
        const uint8_t *__restrict__ tape, float *__restrict__ obs, int32_t *__restrict__ reward,
        uint8_t *__restrict__ done, int32_t *__restrict__ lines, int32_t *status, int flags, F8 dirs)
 {
-    __shared__ uint32_t s_ori[32], s_piece[16];
-    stage_tables(s_ori, s_piece);
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= sv.n_env) return;
+    __shared__ StepSmem<C, R, TILE> sm;
+    const int tid = threadIdx.x;
+    if (tid < kNumOris) sm.ori[tid] = c_ori[tid];
+    if (tid < kNumPieces) sm.piece[tid] = c_piece[tid];
+    if (tid < 2) sm.n_list[tid] = 0;
+    for (int m = tid; m < RunTab<R>::SIZE; m += TILE) sm.run[m] = g_run<R>.v[m];
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * TILE + tid;
+    const bool in_range = e < sv.n_env;
     uint32_t col[C];
-    load_board<C, R>(sv, e, col);
-    Meta mt = unpack_meta(sv.meta[e]);
-    uint2 ep = sv.epi[e];
-    const bool live = mt.piece < kNumPieces;                                  // not a finished rollout fork
-    const uint32_t pw = s_piece[live ? mt.piece : 0];
-    const int action = actions[e];
-    const unsigned long long vm = live ? valid_mask<C, R>(col, pw, s_ori) : 0ull;   // game.py:69
-    int sel = -1;
-    if (action >= 0) {
-        if (flags & TB_FLAG_ACTION_IS_SLOT) {
-            if (action < 64 && ((vm >> action) & 1ull)) sel = action;
-        } else if (action < __popcll(vm)) {
-            sel = nth_set_bit(vm, action);                                    // game.py:83
-        }
-    }
-    if (sel < 0) {
-        // IndexError in the reference (game.py:83).  The env is left untouched, its outputs are defined (zero
-        // observation / reward / lines; done = it has no legal placement at all), and status reports the lowest
-        // offending env as 0x7FFFFFFF - env.
-        if (status) atomicMax(status, 0x7FFFFFFF - (int)(e < 0x7FFFFFFE ? e : 0x7FFFFFFE));
-        if (!(flags & TB_FLAG_VALIDATE_ONLY)) {
-            if (obs) {
-                float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
-                o[0] = make_float4(0.f, 0.f, 0.f, 0.f); o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    Meta mt; mt.piece = kPieceVoid; mt.bag = 0u; mt.draws = 0u;
+    uint2 ep = make_uint2(0u, 0u);
+    bool listed = false, go = false;
+    int lc = 0;
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        listed = false;
+        if (pass == 0) {
+            if (in_range) {
+                load_board<C, R>(sv, e, col);
+                mt = unpack_meta(sv.meta[e]);
+                ep = sv.epi[e];
+                listed = mt.piece < kNumPieces && max_height<C>(col) + 4 > R;
             }
-            if (reward) reward[e] = 0;
-            if (done) done[e] = (uint8_t)(vm == 0ull);
-            if (lines) lines[e] = 0;
+        } else {
+            // ---- the action (game.py:83), against the legal slots of the env's piece
+            const bool live = mt.piece < kNumPieces;                          // not a finished rollout fork
+            const uint32_t pw = sm.piece[live ? mt.piece : 0];
+            unsigned long long vm = 0ull;
+            if (live) vm = max_height<C>(col) + 4 > R ? sm.vmask[tid] : (1ull << piece_num_slots(pw, C)) - 1ull;
+            int sel = -1;
+            if (in_range) {
+                const int action = actions[e];
+                if (action >= 0) {
+                    if (flags & TB_FLAG_ACTION_IS_SLOT) {
+                        if (action < 64 && ((vm >> action) & 1ull)) sel = action;
+                    } else if (action < __popcll(vm)) {
+                        sel = nth_set_bit(vm, action);
+                    }
+                }
+                if (sel < 0) {
+                    // IndexError in the reference (game.py:83).  The env is left untouched, its outputs are defined (zero
+                    // observation / reward / lines; done = it has no legal placement at all), and status reports the
+                    // lowest offending env as 0x7FFFFFFF - env.
+                    if (status) atomicMax(status, 0x7FFFFFFF - (int)(e < 0x7FFFFFFE ? e : 0x7FFFFFFE));
+                    if (!(flags & TB_FLAG_VALIDATE_ONLY)) {
+                        if (obs) {
+                            float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
+                            o[0] = make_float4(0.f, 0.f, 0.f, 0.f); o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (reward) reward[e] = 0;
+                        if (done) done[e] = (uint8_t)(vm == 0ull);
+                        if (lines) lines[e] = 0;
+                    }
+                }
+            }
+            if (flags & TB_FLAG_VALIDATE_ONLY) return;                        // dry run (kernel-uniform): status only
+            go = sel >= 0;
+            if (go) {
+                int ori, c;
+                slot_to_placement(pw, C, sel, ori, c);
+                Eval ev;
+                eval_slow<C, R>(col, sm.ori[ori], c, ev, col, sm.run);        // current_state = afterstates[action]
+                lc = popc32(ev.full);                                         // game.py:85
+                if (obs) {                                                    // game.py:91 (stored here: fewer live registers)
+                    float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
+                    o[0] = make_float4(ev.f[0] * dirs.v[0], ev.f[1] * dirs.v[1], ev.f[2] * dirs.v[2], ev.f[3] * dirs.v[3]);
+                    o[1] = make_float4(ev.f[4] * dirs.v[4], ev.f[5] * dirs.v[5], ev.f[6] * dirs.v[6], ev.f[7] * dirs.v[7]);
+                }
+                if (lines) lines[e] = lc;
+                mt.piece = draw_piece(piece_set, env_key(seed, (uint64_t)(env_offset + e)), mt, tape, e);   // game.py:87
+                listed = mt.piece < kNumPieces && max_height<C>(col) + 4 > R; // else: every slot of the new piece is legal
+            }
         }
-        return;
+        if (listed) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) sm.cols[tid][k] = col[k];
+            sm.lpiece[tid] = (uint8_t)mt.piece;
+            sm.list[atomicAdd(&sm.n_list[pass], 1)] = (uint16_t)tid;
+        }
+        __syncthreads();
+        // ---- pooled: legal slots of the listed envs (game.py:69 / :94-100), one thread per list entry.  (A warp per entry
+        // with lane = enumeration slot shortens the wait at the barrier but issues more instructions in total:
+        // 0.148 ms against 0.122 ms per 2^20 envs, profiles/README.md r2f.)
+        if (tid < sm.n_list[pass]) {
+            const int env = (int)sm.list[tid];
+            uint32_t c2[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) c2[k] = sm.cols[env][k];
+            sm.vmask[env] = valid_slots<C, R>(c2, sm.piece[sm.lpiece[env]], sm.ori);
+        }
+        __syncthreads();
     }
-    if (flags & TB_FLAG_VALIDATE_ONLY) return;                                // dry run: only the status is produced
-    int ori, c;
-    slot_to_placement(pw, C, sel, ori, c);
-    Eval ev;
-    eval_slow<C, R>(col, s_ori[ori], c, ev, col);                             // current_state = afterstates[action]
-    const int lc = popc32(ev.full);                                           // game.py:85
-    int rew = lc - 1;                                                         // game.py:86
-    const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
-    mt.piece = draw_piece(piece_set, key, mt, tape, e);                       // game.py:87
-    const bool dn = mt.piece >= kNumPieces || !any_valid<C, R>(col, s_piece[mt.piece], s_ori);   // game.py:88,94-100
-    if (dn) rew -= 100;                                                       // game.py:89-90
+    if (!go) return;
+    // ---- finish: game over (game.py:88), reward, auto-reset (example_play.py:20-21), stores
+    const bool dn = mt.piece >= kNumPieces || (listed && sm.vmask[tid] == 0ull);
+    int rew = lc - 1 - (dn ? 100 : 0);                                        // game.py:86,89-90
     ep.x += 1u; ep.y += (uint32_t)lc;
-    if (obs) {
-        float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
-        o[0] = make_float4(ev.f[0] * dirs.v[0], ev.f[1] * dirs.v[1], ev.f[2] * dirs.v[2], ev.f[3] * dirs.v[3]);
-        o[1] = make_float4(ev.f[4] * dirs.v[4], ev.f[5] * dirs.v[5], ev.f[6] * dirs.v[6], ev.f[7] * dirs.v[7]);
-    }
     if (reward) reward[e] = rew;
     if (done) done[e] = (uint8_t)dn;
-    if (lines) lines[e] = lc;
-    if (dn && (flags & TB_FLAG_AUTO_RESET) && !tape) {                        // example_play.py:20-21
+    if (dn && (flags & TB_FLAG_AUTO_RESET) && !tape) {
 #pragma unroll
         for (int k = 0; k < C; ++k) col[k] = 0u;
-        mt.piece = draw_piece(piece_set, key, mt, nullptr, e);
+        mt.piece = draw_piece(piece_set, env_key(seed, (uint64_t)(env_offset + e)), mt, nullptr, e);
         ep = make_uint2(0u, 0u);
     }
     store_board<C, R>(sv, e, col);
@@ -693,6 +822,48 @@ __device__ __forceinline__ void stats_flush(const LaneStats &s, long long *s_blk
     }
 }
 
+// Episode statistics of one step, aggregated over the warp into its shared-memory vector (ballots are warp-uniform; lane 0
+// accumulates).  Must be reached by the whole warp.  placed: the lane's env made a placement; dn: it ended its episode
+// with it (ep_done = the finished episode's placements / lines); lc: lines cleared; n_slots: afterstates enumerated.
+__device__ __forceinline__ void warp_step_stats(long long *wstat, int lane, bool placed, bool dn, int lc, int n_slots,
+                                                uint2 ep_done)
+{
+    const unsigned bp = __ballot_sync(FULLMASK, placed), bd = __ballot_sync(FULLMASK, dn);
+    const unsigned b1 = __ballot_sync(FULLMASK, lc == 1), b2 = __ballot_sync(FULLMASK, lc == 2);
+    const unsigned b3 = __ballot_sync(FULLMASK, lc == 3), b4 = __ballot_sync(FULLMASK, lc == 4);
+    const int n_after = __reduce_add_sync(FULLMASK, n_slots);
+    long long se = 0, sl = 0, me = 0, ml = 0;
+    if (bd) {
+        se = warp_sum(dn ? (long long)ep_done.x : 0ll); sl = warp_sum(dn ? (long long)ep_done.y : 0ll);
+        me = warp_max(dn ? (long long)ep_done.x : 0ll); ml = warp_max(dn ? (long long)ep_done.y : 0ll);
+    }
+    if (lane == 0) {
+        const int np_ = __popc(bp), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3), n4 = __popc(b4);
+        const int nd = __popc(bd), nl = n1 + 2 * n2 + 3 * n3 + 4 * n4;
+        wstat[TB_ST_PLACEMENTS] += np_; wstat[TB_ST_EPISODES] += nd; wstat[TB_ST_LINES] += nl;
+        wstat[TB_ST_REWARD] += nl - np_ - 100 * nd; wstat[TB_ST_AFTERSTATES] += n_after;
+        wstat[TB_ST_LINES0] += np_ - n1 - n2 - n3 - n4; wstat[TB_ST_LINES1] += n1; wstat[TB_ST_LINES2] += n2;
+        wstat[TB_ST_LINES3] += n3; wstat[TB_ST_LINES4] += n4;
+        if (bd) {
+            wstat[TB_ST_SUM_EP_STEPS] += se; wstat[TB_ST_SUM_EP_LINES] += sl;
+            if (me > wstat[TB_ST_MAX_EP_STEPS]) wstat[TB_ST_MAX_EP_STEPS] = me;
+            if (ml > wstat[TB_ST_MAX_EP_LINES]) wstat[TB_ST_MAX_EP_LINES] = ml;
+        }
+    }
+}
+// a warp's statistics vector -> global (sums, the two maxima by max)
+__device__ __forceinline__ void warp_stats_to_global(const long long *wstat, int lane, int64_t *stats)
+{
+    __syncwarp();
+    if (lane < TB_ST_COUNT) {
+        const long long r = wstat[lane];
+        if (r != 0) {
+            if (lane == TB_ST_MAX_EP_LINES || lane == TB_ST_MAX_EP_STEPS) atomicMax((long long *)&stats[lane], r);
+            else atomicAdd((unsigned long long *)&stats[lane], (unsigned long long)r);
+        }
+    }
+}
+
 // Apply the chosen placement to the lane's env: lock, clear, reward, next piece, game-over, auto-reset.
 // Returns the legal-slot mask of the NEW piece on the NEW board (never 0: a finished env is reset in place).
 template <int C, int R>
@@ -728,6 +899,9 @@ apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece
     return vm;
 }
 
+// (Round 2 tried the K2 scheme here -- a CTA steps a tile of envs in lockstep and pools the legality test of its tall envs
+// over the CTA, two barriers per step: 3.31 ms against 2.56 ms per 32 steps of 2^20 envs.  Independent threads with many
+// CTAs per SM hide the divergence better than lockstep removes it; profiles/README.md, r2d.)
 // random policy: everything is per-env, one thread per env, board in registers for all n_steps
 template <int C, int R>
 __global__ void __launch_bounds__(128, 6)                  // 80 registers, no spills (measured: profiles/README.md, r1g)
@@ -935,7 +1109,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
                 const int aslot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
                 Eval ev;
-                eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr);
+                eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr,
+                                sm.run);                   // legal placements only: non-terminal, wells by table
                 atomicMax(&bs.best[oslot], score_key(orderable(fitness(ev.f, wts.v)), aslot));
             });
             if (WPG == 1) __syncwarp();                    // phase C reads the best keys of this warp's envs only
@@ -983,31 +1158,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     ep = make_uint2(0u, 0u);
                 }
             }
-            // episode statistics of the step, aggregated over the warp (ballots are warp-uniform; lane 0 accumulates)
-            {
-                const unsigned bp = __ballot_sync(FULLMASK, placed), bd = __ballot_sync(FULLMASK, dn);
-                const unsigned b1 = __ballot_sync(FULLMASK, lc == 1), b2 = __ballot_sync(FULLMASK, lc == 2);
-                const unsigned b3 = __ballot_sync(FULLMASK, lc == 3), b4 = __ballot_sync(FULLMASK, lc == 4);
-                const int n_after = __reduce_add_sync(FULLMASK, n_slots);
-                long long se = 0, sl = 0, me = 0, ml = 0;
-                if (bd) {
-                    se = warp_sum(dn ? (long long)ep_done.x : 0ll); sl = warp_sum(dn ? (long long)ep_done.y : 0ll);
-                    me = warp_max(dn ? (long long)ep_done.x : 0ll); ml = warp_max(dn ? (long long)ep_done.y : 0ll);
-                }
-                if (lane == 0) {
-                    const int np_ = __popc(bp), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3), n4 = __popc(b4);
-                    const int nd = __popc(bd), nl = n1 + 2 * n2 + 3 * n3 + 4 * n4;
-                    wstat[TB_ST_PLACEMENTS] += np_; wstat[TB_ST_EPISODES] += nd; wstat[TB_ST_LINES] += nl;
-                    wstat[TB_ST_REWARD] += nl - np_ - 100 * nd; wstat[TB_ST_AFTERSTATES] += n_after;
-                    wstat[TB_ST_LINES0] += np_ - n1 - n2 - n3 - n4; wstat[TB_ST_LINES1] += n1; wstat[TB_ST_LINES2] += n2;
-                    wstat[TB_ST_LINES3] += n3; wstat[TB_ST_LINES4] += n4;
-                    if (bd) {
-                        wstat[TB_ST_SUM_EP_STEPS] += se; wstat[TB_ST_SUM_EP_LINES] += sl;
-                        if (me > wstat[TB_ST_MAX_EP_STEPS]) wstat[TB_ST_MAX_EP_STEPS] = me;
-                        if (ml > wstat[TB_ST_MAX_EP_LINES]) wstat[TB_ST_MAX_EP_LINES] = ml;
-                    }
-                }
-            }
+            warp_step_stats(wstat, lane, placed, dn, lc, n_slots, ep_done);
         }
         if (in_range && (active || mt.piece == kPieceDead)) {
             store_board<C, R>(sv, e, col);
@@ -1015,15 +1166,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             sv.epi[e] = ep;
         }
     }
-    // per-warp statistics -> global
-    __syncwarp();
-    if (lane < TB_ST_COUNT) {
-        const long long r = wstat[lane];
-        if (r != 0) {
-            if (lane == TB_ST_MAX_EP_LINES || lane == TB_ST_MAX_EP_STEPS) atomicMax((long long *)&stats[lane], r);
-            else atomicAdd((unsigned long long *)&stats[lane], (unsigned long long)r);
-        }
-    }
+    warp_stats_to_global(wstat, lane, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1221,7 +1364,7 @@ static inline unsigned grid_for(const TbLaunchCtx *cx, int64_t work_items, int p
 // Tile configuration by batch size: the throughput configuration (cfg 0, 256-env tiles, thread per env) once there is
 // at least one tile per SM; below that 128-env tiles (`mid`); and for batches of at most cx->small_groups (default 4)
 // 32-env groups per SM the small-batch configuration 4 (32 envs and 4 warps per CTA: shortest critical path).
-//   K1 cfg  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5   6: 256 x 4
+//   K1 cfg  0: 256-thread CTAs, 3 per SM, <= 85 registers (default)   2: 256 x 2, 128 registers   3: 128 x 5
 //   K3 cfg  0: 256 x 3, 80 registers (default)   2: 128 x 4   3: 128 x 5   7: 256 x 2, 125 registers
 //   both    4: 32 envs x 128 threads   5: 64 envs x 256 threads   (several warps per 32-env group, small batches)
 static inline int small_batch_cfg(const TbLaunchCtx *cx, int64_t n_env, int mid)
@@ -1257,18 +1400,15 @@ struct ShapeOps {
         // small batches (fewer 256-env tiles than SMs) use 128-env tiles: twice the CTAs, half the per-tile latency
         const int cfg = cx->k1_cfg >= 0 ? cx->k1_cfg : small_batch_cfg(cx, n_env, 3);
         kern_t kern; size_t smem; int tile, minb, threads = 0;
-        if (cfg == 4) { tile = 32; threads = 128; minb = 4; smem = sizeof(CtaSmem<C, R, 32>);
-            kern = directions ? k_afterstates<C, R, true, 32, 4, 128> : k_afterstates<C, R, false, 32, 4, 128>; }
-        else if (cfg == 5) { tile = 64; threads = 256; minb = 2; smem = sizeof(CtaSmem<C, R, 64>);
-            kern = directions ? k_afterstates<C, R, true, 64, 2, 256> : k_afterstates<C, R, false, 64, 2, 256>; }
-        else if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<C, R, 128>);
-            kern = directions ? k_afterstates<C, R, true, 128, 5> : k_afterstates<C, R, false, 128, 5>; }
-        else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<C, R, 256>);
-            kern = directions ? k_afterstates<C, R, true, 256, 2> : k_afterstates<C, R, false, 256, 2>; }
-        else if (cfg == 6) { tile = 256; minb = 4; smem = sizeof(CtaSmem<C, R, 256>);
-            kern = directions ? k_afterstates<C, R, true, 256, 4> : k_afterstates<C, R, false, 256, 4>; }
-        else { tile = 256; minb = 3; smem = sizeof(CtaSmem<C, R, 256>);
-            kern = directions ? k_afterstates<C, R, true, 256, 3> : k_afterstates<C, R, false, 256, 3>; }
+        const int fmt = (flags & TB_FLAG_FEATS_I16) ? kFmtI16 : (directions ? kFmtF32Dirs : kFmtF32);
+#define TB_K1_KERNEL(...) (fmt == kFmtI16 ? k_afterstates<C, R, kFmtI16, __VA_ARGS__> : fmt == kFmtF32Dirs ? \
+                           k_afterstates<C, R, kFmtF32Dirs, __VA_ARGS__> : k_afterstates<C, R, kFmtF32, __VA_ARGS__>)
+        if (cfg == 4) { tile = 32; threads = 128; minb = 4; smem = sizeof(CtaSmem<C, R, 32>); kern = TB_K1_KERNEL(32, 4, 128); }
+        else if (cfg == 5) { tile = 64; threads = 256; minb = 2; smem = sizeof(CtaSmem<C, R, 64>); kern = TB_K1_KERNEL(64, 2, 256); }
+        else if (cfg == 3) { tile = 128; minb = 5; smem = sizeof(CtaSmem<C, R, 128>); kern = TB_K1_KERNEL(128, 5); }
+        else if (cfg == 2) { tile = 256; minb = 2; smem = sizeof(CtaSmem<C, R, 256>); kern = TB_K1_KERNEL(256, 2); }
+        else { tile = 256; minb = 3; smem = sizeof(CtaSmem<C, R, 256>); kern = TB_K1_KERNEL(256, 3); }
+#undef TB_K1_KERNEL
         if (opt_in_smem(cx, (const void *)kern, smem)) return -2;
         kern<<<grid_for(cx, n_env, tile, minb, 8), threads ? threads : tile, smem, (cudaStream_t)cx->stream>>>(
             view(state, n_env), (float *)feats_out, (unsigned long long *)valid_out, count_out, a_stride, dirs, flags);
@@ -1288,9 +1428,18 @@ struct ShapeOps {
                     const int32_t *actions, const uint8_t *tape, float *obs, int32_t *reward, uint8_t *done,
                     int32_t *lines, int32_t *status, int flags)
     {
-        k_step<C, R><<<(unsigned)((n_env + 127) / 128), 128, 0, (cudaStream_t)cx->stream>>>(
-            view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags,
-            f8_from(nullptr, 1.0f));
+        // k2_cfg (tuning): 0 = 256 envs x 4 CTAs per SM (default), 1 = 128 x 8, 2 = 256 x 3
+        const F8 one = f8_from(nullptr, 1.0f);
+        cudaStream_t st = (cudaStream_t)cx->stream;
+        if (cx->k2_cfg == 1)
+            k_step<C, R, 128, 8><<<(unsigned)((n_env + 127) / 128), 128, 0, st>>>(
+                view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
+        else if (cx->k2_cfg == 2)
+            k_step<C, R, 256, 3><<<(unsigned)((n_env + 255) / 256), 256, 0, st>>>(
+                view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
+        else
+            k_step<C, R, 256, 4><<<(unsigned)((n_env + 255) / 256), 256, 0, st>>>(
+                view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
         return check_launch(cx, "tb_step");
     }
 

@@ -11,13 +11,14 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#define TB_SHAPE_ABI 3          /* bumped whenever TbShapeVT / TbLaunchCtx change */
+#define TB_SHAPE_ABI 5          /* bumped whenever TbShapeVT / TbLaunchCtx change */
 
 /* what every launcher needs besides its arguments */
 typedef struct TbLaunchCtx {
     void *stream;               /* cudaStream_t */
     int sm_count;
     int k1_cfg, k3_cfg;         /* tile configuration of K1 / K3: -1 = by batch size (what ships), else forced (tests) */
+    int k2_cfg, k3r_cfg;        /* CTA shape of K2 / of the random rollout: -1 / 0 = default */
     int small_groups;           /* 32-env groups per SM up to which the small-batch configuration is used */
     int max_ctas;               /* 0 = no cap; tests cap the grid so that every CTA loops over several tiles */
     char *err;                  /* error message buffer (thread-local in the ABI object) */
