@@ -17,16 +17,17 @@
  *     threads on distinct streams / devices.
  *   - board shape (num_columns C, num_rows R) selects a compiled template instantiation (one translation unit per
  *     shape, csrc/tb_shape.cu); tb_supported_shape() says which are loaded (built in: 10x20, 10x10, 6x12, 8x16, 4x4,
- *     16x28, 12x24).  The reference takes any num_columns / num_rows (game.py:21-31): any other shape with
- *     4 <= C <= 16 and 4 <= R <= 28 (uint16 row masks, 32-bit column masks) is compiled into its own shared object
- *     and added with tb_load_shape().
+ *     16x27, 12x24).  The reference takes any num_columns / num_rows (game.py:21-31): any other shape with
+ *     4 <= C <= 16 and 4 <= R <= 27 (uint16 row masks; 32-bit column masks with one spare bit) is compiled into its
+ *     own shared object and added with tb_load_shape().
  *
  * Device state ("state" below) is one caller-owned allocation of tb_state_bytes() bytes, 256-byte
  * aligned, laid out as a structure of arrays over envs:
  *   planes  uint4[NB][n_env]   row masks, uint16 per row (bit c = cell (r, c)), 8 rows per 128-bit word,
  *                              NB = ceil((R + 4) / 8)
- *   meta    uint4[n_env]       bytes 0..9 column heights (lowest_free_rows, state.py:162-172),
- *                              byte 10 current piece (global id), byte 11 bag mask, bytes 12..15 draw counter
+ *   meta    uint4[n_env]       bytes 0..9 column heights (lowest_free_rows, state.py:162-172; boards of up to 10
+ *                              columns -- wider boards leave them zero, tb_export_boards derives heights from the
+ *                              planes), byte 10 current piece (global id), byte 11 bag mask, bytes 12..15 draw counter
  *   epi     uint2[n_env]       placements and lines of the running episode
  *
  * Piece ids (global): 0 Straight, 1 RCorner, 2 LCorner, 3 Square, 4 SnakeR, 5 SnakeL, 6 T   (game.py:41-47)
@@ -48,7 +49,7 @@ extern "C" {
 
 #define TB_VERSION 200          /* 0.2.0 */
 #define TB_NUM_FEATURES 8
-#define TB_MAX_SLOTS 36         /* ThreeL at C = 10 */
+#define TB_MAX_SLOTS 60         /* ThreeL at C = 16 (36 at C = 10); per-slot masks are 64 bits */
 
 /* tb_step / tb_afterstates flags */
 #define TB_FLAG_AUTO_RESET     1   /* step: reset a finished env in place (what example_play.py:20-21 does) */

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liboracle.so")
 
-MAX_A = 40
+MAX_A = 64
 STATS = ("placements", "episodes", "lines", "reward", "afterstates",
          "lines0", "lines1", "lines2", "lines3", "lines4",
          "max_ep_lines", "max_ep_steps", "sum_ep_steps", "sum_ep_lines", "reserved0", "reserved1")

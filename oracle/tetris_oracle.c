@@ -27,7 +27,7 @@
 
 #define ORC_MAX_N 32   /* stored rows  = num_rows + 4 (game.py:56)          */
 #define ORC_MAX_C 16   /* columns                                             */
-#define ORC_MAX_A 40   /* afterstates per piece (36 at C=10 for ThreeL)       */
+#define ORC_MAX_A 64   /* afterstates per piece (36 at C=10, 60 at C=16: ThreeL) */
 
 /* ------------------------------------------------------------------------ */
 /* Piece x orientation tables, transcribed from tetromino.py.                */

@@ -237,8 +237,8 @@ def dense_board(rng, C, R, kind):
 
 
 def gen_afterstates_dense(ref):
-    """afterstates_dense.npz: >= 80 k afterstates on near-full boards of five shapes (the three of BASELINE.json plus
-    8x16 and 4x4), all nine pieces -- hundreds of multi-line clears incl. four-line clears, terminal placements
+    """afterstates_dense.npz: > 100 k afterstates on near-full boards of eight shapes (the three of BASELINE.json,
+    8x16, 4x4, and 16x27 / 12x24 / 7x9 beyond the usual sizes), all nine pieces -- hundreds of multi-line clears incl. four-line clears, terminal placements
     rescued by a clear, terminal-with-clear.  Rows are padded to 32, columns to 16."""
     st = ref["state"]
     rng = np.random.default_rng(4321)
@@ -246,7 +246,8 @@ def gen_afterstates_dense(ref):
     per = {k: [] for k in ("feat2", "terminal", "n_cleared", "rows", "heights", "anchor", "is_full")}
     total = 0
     PADN, PADC = 32, 16
-    for (C, R), n_boards in (((10, 20), 150), ((10, 10), 110), ((8, 16), 110), ((6, 12), 130), ((4, 4), 120)):
+    for (C, R), n_boards in (((10, 20), 150), ((10, 10), 110), ((8, 16), 110), ((6, 12), 130), ((4, 4), 120),
+                             ((16, 27), 40), ((12, 24), 50), ((7, 9), 60)):
         pieces = make_pieces(ref, C)
         boards = [dense_board(rng, C, R, "tall" if k % 2 else "mid") for k in range(n_boards)]
         for rep in boards:

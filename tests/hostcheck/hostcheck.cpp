@@ -66,7 +66,7 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
     return n;
 }
 
-#define SHAPES(X) X(10, 20) X(10, 10) X(6, 12) X(8, 16) X(4, 4)
+#define SHAPES(X) X(10, 20) X(10, 10) X(6, 12) X(8, 16) X(4, 4) X(16, 27) X(12, 24) X(7, 9)
 
 extern "C" int hc_afterstates(int C, int R, int piece, const uint16_t *rows, int mode, float *feats,
                               uint8_t *terminal, int32_t *ncleared, uint16_t *rows_out, int32_t *anchor,
@@ -135,5 +135,8 @@ extern "C" int hc_table_images()
     if (!run_image_ok<12>()) return -12;
     if (!run_image_ok<16>()) return -16;
     if (!run_image_ok<4>()) return -4;
+    if (!run_image_ok<27>()) return -27;
+    if (!run_image_ok<24>()) return -24;
+    if (!run_image_ok<9>()) return -9;
     return 0;
 }

@@ -10,7 +10,7 @@ from test_oracle_golden import replay_trace
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(10, 20), (10, 10), (6, 12), (8, 16), (4, 4)]
+SHAPES = [(10, 20), (10, 10), (6, 12), (8, 16), (4, 4), (16, 27), (12, 24), (7, 9)]   # 7x9: loaded as a shape plugin
 
 
 def _torch():
@@ -145,8 +145,8 @@ def test_lockstep_vs_oracle(shape, piece_set):
     from oracle import oracle as orc
     from tetris_b200 import BatchedTetris
     Cc, R = shape
-    n = 4096 if shape == (10, 20) else 1024
-    steps = 200 if shape == (10, 20) else 80
+    n = 4096 if shape == (10, 20) else (512 if Cc > 10 else 1024)
+    steps = 200 if shape == (10, 20) else (120 if R > 20 else 80)
     seed = 0x5EED
     env = BatchedTetris(Cc, R, n, piece_set=piece_set, seed=seed)
     ob = orc.Batch(Cc, R, n, piece_set=piece_set, seed=seed)
@@ -178,15 +178,15 @@ def test_lockstep_vs_oracle(shape, piece_set):
 
 
 @pytest.mark.parametrize("policy", ["random", "greedy"])
-@pytest.mark.parametrize("shape", [(10, 20), (10, 10), (6, 12), (4, 4)])
+@pytest.mark.parametrize("shape", [(10, 20), (10, 10), (6, 12), (4, 4), (16, 27), (7, 9)])
 def test_rollout_vs_oracle(shape, policy):
     """Fused rollout kernels (in-kernel policy, RNG, game-over, auto-reset) against the oracle's loop: identical
     final boards/pieces/counters and identical episode statistics."""
     from oracle import oracle as orc
     from tetris_b200 import BatchedTetris
     Cc, R = shape
-    n, seed = 2048 + 17, 77            # not a multiple of 32: exercises the ragged last warp tile
-    T = 40 if policy == "random" else 25
+    n, seed = (2048 if Cc <= 10 else 512) + 17, 77     # not a multiple of 32: exercises the ragged last warp tile
+    T = (40 if policy == "random" else 25) * (3 if R > 20 else 1)
     env = BatchedTetris(Cc, R, n, piece_set=1, seed=seed, env_offset=5)
     ob = orc.Batch(Cc, R, n, piece_set=1, seed=seed, env_offset=5)
     ob.reset()
@@ -200,7 +200,7 @@ def test_rollout_vs_oracle(shape, policy):
         _compare_state(env, ob)
         assert np.array_equal(env.stats.cpu().numpy(), total), rnd
     assert total[0] == 3 * T * n
-    if policy == "random" or shape != (10, 20):
+    if policy == "random" or shape not in ((10, 20), (16, 27)):
         assert total[1] > 0                                # episodes ended and were auto-reset
 
 
@@ -710,3 +710,33 @@ def test_compact_features():
                 assert torch.equal(h[mask].float() * 0.5, f[mask]), (Cc, R, dirs, term)
                 assert int(mask.sum()) > 5 * n
         env.set_directions(None)
+
+
+def test_render_any_env_and_wide_board(capsys):
+    """BatchedTetris.render(env) / board_string(env): utils.print_board_to_string (utils.py:179-191, the 4 buffer rows
+    included) for any env of a batch, on a 16-column board; and the reference-shaped Tetris class on a size outside the
+    built-in list (game.py:21-31 takes any num_columns / num_rows)."""
+    from tetris_b200 import BatchedTetris
+    env = BatchedTetris(16, 27, 50, piece_set=1, seed=3)
+    env.rollout(40, "random")
+    rep = env.representation(17)
+    assert rep.shape == (31, 16) and rep.dtype == np.int64 and rep.any()
+    text = env.board_string(17)
+    lines = text.strip("\n").split("\n")
+    assert len(lines) == 31 and all(len(ln) == 2 + 2 * 16 for ln in lines)
+    assert [[ch != " " for ch in ln[1:-1][::2]] for ln in lines] == (rep[::-1] != 0).tolist()
+    env.render(17)
+    out = capsys.readouterr().out
+    assert text.strip("\n") in out and any(name in out for name in ("Straight", "RCorner", "LCorner", "Square", "SnakeR", "SnakeL", "T"))
+    assert np.array_equal(env.heights[17], [(np.nonzero(rep[:, c])[0].max() + 1) if rep[:, c].any() else 0 for c in range(16)])
+    from tetris.game import Tetris
+    np.random.seed(1)
+    g = Tetris(7, 9)
+    total = 0
+    for _ in range(30):
+        feats, _none = g.get_after_states()
+        obs, rew, done, lines_ = g.step(int(np.argmax(feats.sum(axis=1))))
+        total += rew
+        if done:
+            g.reset()
+    assert g.current_state.representation.shape == (13, 7)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
 SO = os.path.join(HERE, "hostcheck", "libhostcheck.so")
 CORE = os.path.join(os.path.dirname(HERE), "tetris_b200", "csrc", "tb_core.cuh")
-SHAPES = [(10, 20), (10, 10), (6, 12), (8, 16), (4, 4)]
+SHAPES = [(10, 20), (10, 10), (6, 12), (8, 16), (4, 4), (16, 27), (12, 24), (7, 9)]
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +39,7 @@ def hc():
 
 def hc_afterstates(L, Cc, R, piece, rows, mode):
     N = R + 4
-    A = 40
+    A = 64
     feats = np.zeros((A, 8), np.float32)
     term = np.zeros(A, np.uint8)
     ncl = np.zeros(A, np.int32)
@@ -186,7 +186,7 @@ def test_fitness(hc):
 
 
 def test_num_slots(hc):
-    for Cc in (4, 6, 8, 10):
+    for Cc in (4, 6, 7, 8, 10, 12, 16):
         for p in range(9):
             assert hc.hc_num_slots(p, Cc) == orc.num_afterstates(p, Cc)
 

@@ -23,8 +23,8 @@ def test_empty_board_features():
 @pytest.mark.parametrize("name,at_least", [("afterstates", 30000), ("afterstates_dense", 80000)])
 def test_afterstates_fixture(name, at_least):
     """`afterstates`: played and arbitrary boards of 10x20 / 10x10 / 6x12.  `afterstates_dense`: near-full stacks of
-    those three plus 8x16 and 4x4 -- 115 four-line clears, 875 placements that poke above row R and are rescued by
-    the clear, 353 that clear and are terminal all the same (tests/golden/make_golden.py prints the census)."""
+    those three plus 8x16, 4x4, 16x27, 12x24 and 7x9 -- over a hundred four-line clears, about a thousand placements that
+    poke above row R and are rescued by the clear, hundreds that clear and are terminal all the same (tests/golden/make_golden.py prints the census)."""
     g = load(name)
     n_checked = 0
     for i in range(len(g["piece"])):
@@ -48,7 +48,7 @@ def test_afterstates_fixture(name, at_least):
     if name == "afterstates_dense":
         ncl = g["a_n_cleared"]
         assert (ncl == 4).sum() >= 50 and (ncl == 3).sum() >= 50 and (g["a_terminal"] & (ncl > 0)).sum() >= 50
-        assert {tuple(x) for x in g["shape"].tolist()} == {(10, 20), (10, 10), (6, 12), (8, 16), (4, 4)}
+        assert {tuple(x) for x in g["shape"].tolist()} == {(10, 20), (10, 10), (6, 12), (8, 16), (4, 4), (16, 27), (12, 24), (7, 9)}
 
 
 def replay_trace(g, make_batch, rng_mode):

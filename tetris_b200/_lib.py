@@ -13,8 +13,8 @@ _INC = os.path.join(os.path.dirname(_HERE), "include", "tetris_b200.h")
 SHAPE_DEPS = [os.path.join(CSRC, f) for f in ("tb_shape.cu", "tb_kernels.cuh", "tb_core.cuh", "tb_shape.h")] + [_INC]
 ABI_DEPS = [os.path.join(CSRC, f) for f in ("tb_abi.cu", "tb_core.cuh", "tb_shape.h")] + [_INC]
 SOURCES = sorted(set(SHAPE_DEPS + ABI_DEPS))
-# board shapes linked into libtetris_b200.so (columns, rows); any other 4..16 x 4..28 shape: build_shape() + tb_load_shape
-BUILTIN_SHAPES = ((10, 20), (10, 10), (6, 12), (8, 16), (4, 4))
+# board shapes linked into libtetris_b200.so (columns, rows); any other 4..16 x 4..27 shape: build_shape() + tb_load_shape
+BUILTIN_SHAPES = ((10, 20), (10, 10), (6, 12), (8, 16), (4, 4), (16, 27), (12, 24))
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 BUILD_DIR = os.path.join(CSRC, "build")
@@ -134,8 +134,8 @@ def shape_plugin_path(c, r):
 def build_shape(c, r, force=False):
     """Compile the kernels of one more board shape into their own in-tree shared object (needs nvcc; ~1 minute)."""
     c, r = int(c), int(r)
-    if not (4 <= c <= 16 and 4 <= r <= 28):
-        raise ValueError("board shape %dx%d is outside 4..16 columns x 4..28 rows (uint16 row masks, 32-bit column masks)" % (c, r))
+    if not (4 <= c <= 16 and 4 <= r <= 27):
+        raise ValueError("board shape %dx%d is outside 4..16 columns x 4..27 rows (uint16 row masks, 32-bit column masks)" % (c, r))
     path = shape_plugin_path(c, r)
     if force or _newer(SHAPE_DEPS, path):
         subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-shared", "-I", CSRC, "-o", path, _shape_stub(c, r, plugin=True)],

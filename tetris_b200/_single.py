@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 
-A_STRIDE = 36        # TB_MAX_SLOTS
+A_STRIDE = 64        # >= TB_MAX_SLOTS (60: ThreeL on 16 columns)
 _ctx = {}
 
 

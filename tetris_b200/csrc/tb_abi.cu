@@ -123,15 +123,15 @@ __global__ void k_combine_stats(const long long *__restrict__ parts, int n_parts
 using namespace tb;
 
 // Board shapes linked into this library: the three of BASELINE.json's configs, two extras (mid-size, tiny edge case)
-// and two beyond the reference's usual sizes (wide / tall: up to 16 columns and 28 rows fit the uint16 row masks and
-// 32-bit column masks).  Any other shape with 4 <= C <= 16, 4 <= R <= 28 can be compiled into its own shared object
+// and two beyond the reference's usual sizes (wide / tall: up to 16 columns and 27 rows fit the uint16 row masks and
+// 32-bit column masks).  Any other shape with 4 <= C <= 16, 4 <= R <= 27 can be compiled into its own shared object
 // (tetris_b200._lib.build_shape) and added with tb_load_shape().
 // The list is generated by the build (tetris_b200/_lib.py: BUILTIN_SHAPES -> build/tb_builtin_shapes.inc).
 #if !defined(TB_BUILTIN_SHAPES) && __has_include("build/tb_builtin_shapes.inc")
 #include "build/tb_builtin_shapes.inc"
 #endif
 #ifndef TB_BUILTIN_SHAPES
-#define TB_BUILTIN_SHAPES(X) X(10, 20) X(10, 10) X(6, 12) X(8, 16) X(4, 4) X(16, 28) X(12, 24)
+#define TB_BUILTIN_SHAPES(X) X(10, 20) X(10, 10) X(6, 12) X(8, 16) X(4, 4) X(16, 27) X(12, 24)
 #endif
 #define X(c, r) extern "C" const TbShapeVT *tb_shape_vt_##c##x##r(void);
 TB_BUILTIN_SHAPES(X)

@@ -259,8 +259,10 @@ struct Shape {
     static constexpr int NW = NB * 4;                    // packed 32-bit words per env
     static constexpr uint32_t ALL = (N >= 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
     static constexpr uint32_t FULLROW = (1u << C) - 1u;
-    static_assert(C >= 4 && C <= 10, "supported widths: 4..10 columns");
-    static_assert(N <= 24 && R >= 4, "supported heights: 4..20 rows (+4 buffer rows)");
+    // uint16 row masks hold 16 columns; 32-bit column masks hold R + 4 stored rows.  R + 4 <= 31 (not 32) keeps every
+    // shift amount in the code below 32 -- a terminal afterstate's column can be R + 4 cells tall.
+    static_assert(C >= 4 && C <= 16, "supported widths: 4..16 columns");
+    static_assert(N <= 31 && R >= 4, "supported heights: 4..27 rows (+4 buffer rows)");
 };
 
 // rows (packed words w[NW]) -> column masks col[C]
@@ -479,7 +481,7 @@ struct RunTab {
     static constexpr int NCH = R <= 10 ? 1 : (R <= 20 ? 2 : 3);
     static constexpr int HB = (R + NCH - 1) / NCH;
     static constexpr int SIZE = 1 << HB;
-    static_assert(HB <= 10 && R <= 28, "run table: chunks of at most 10 rows, boards of at most 28 rows");
+    static_assert(HB <= 10 && R <= 27, "run table: chunks of at most 10 rows, boards of at most 27 rows");
 };
 template <int R>
 TB_HD uint32_t run_tab_entry(uint32_t m)

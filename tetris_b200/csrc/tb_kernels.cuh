@@ -74,12 +74,16 @@ __device__ __forceinline__ Meta unpack_meta(uint4 m)
     r.draws = m.w;
     return r;
 }
+// meta word: bytes 0..9 column heights (boards of up to 10 columns; wider boards leave them zero -- heights are always
+// derivable from the row planes, which is what tb_export_boards does), byte 10 piece, byte 11 bag, bytes 12..15 draws
 template <int C>
 __device__ __forceinline__ uint4 pack_meta(const uint32_t *col, Meta mt)
 {
     uint32_t w[3] = {0u, 0u, 0u};
+    if (C <= 10) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) w[c >> 2] |= (uint32_t)height_of(col[c]) << (8 * (c & 3));
+        for (int c = 0; c < C; ++c) w[(c >> 2) % 3] |= (uint32_t)height_of(col[c]) << (8 * (c & 3));
+    }
     return make_uint4(w[0], w[1], w[2] | ((uint32_t)mt.piece << 16) | (mt.bag << 24), mt.draws);
 }
 template <int C, int R>
@@ -398,7 +402,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     using K = Env<C, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     static_assert(TILE % 32 == 0 && THREADS % TILE == 0, "TILE: whole warps of envs; THREADS: a multiple of TILE");
-    constexpr int NWARPS = THREADS / 32, NGROUPS = TILE / 32, WPG = NWARPS / NGROUPS;
+    constexpr int NWARPS = THREADS / 32, NGROUPS = TILE / 32;
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
     stage_cta(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1226,25 +1230,25 @@ __global__ void k_export(StateView sv, int64_t first, int64_t count, uint16_t *_
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const int64_t e = first + i;
-    if (rows_out) {
+    if (rows_out || heights_out) {
+        uint32_t w[S::NW];
 #pragma unroll
         for (int b = 0; b < S::NB; ++b) {
             const uint4 v = sv.planes[(int64_t)b * sv.n_env + e];
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            w[4 * b] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
+        }
+        if (rows_out) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int r = 8 * b + k;
-                if (r < S::N) rows_out[i * S::N + r] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
-            }
+            for (int r = 0; r < S::N; ++r) rows_out[i * S::N + r] = (uint16_t)(w[r >> 1] >> (16 * (r & 1)));
+        }
+        if (heights_out) {                                   // lowest_free_rows (state.py:162-172), from the board itself
+            uint32_t col[C];
+            rows_to_cols<C, R>(w, col);
+#pragma unroll
+            for (int c = 0; c < C; ++c) heights_out[i * C + c] = (uint8_t)height_of(col[c]);
         }
     }
-    const uint4 m = sv.meta[e];
-    if (heights_out) {
-        const uint32_t w[3] = {m.x, m.y, m.z};
-#pragma unroll
-        for (int c = 0; c < C; ++c) heights_out[i * C + c] = (uint8_t)((w[c >> 2] >> (8 * (c & 3))) & 0xffu);
-    }
-    if (piece_out) piece_out[i] = (uint8_t)((m.z >> 16) & 0xffu);
+    if (piece_out) piece_out[i] = (uint8_t)((sv.meta[e].z >> 16) & 0xffu);
 }
 
 template <int C, int R>
