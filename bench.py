@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--board", default="10x20", help="columns x rows: 10x20 (headline), 10x10, 6x12, 8x16")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="stream-pipelined chunks of the host-buffer e2e cycle")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu baseline / e2e side measurements")
+    ap.add_argument("--extras", default="full", choices=["full", "light", "none"],
+                    help="light: only the per-kernel rooflines beside the timed step (board sweeps)")
     return ap.parse_args()
 
 
@@ -131,21 +133,37 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def integer_pipe(prof, k1_ms):
-    """The binding roof of K1: the integer ALU pipe.  Peak = LOP3 throughput measured on a B200 of this pool
-    (profiles/int_peak.json, profiles/microbench/int_peak.cu); achieved = ALU-pipe share of the kernel's executed
-    thread-instructions (ncu capture in profiles/) over the live-timed duration."""
-    out = {"alu_pipe_pct_of_peak_ncu": prof.get("alu_pipe_pct"), "issue_active_pct": prof.get("issue_active_pct"),
-           "source": "ncu --set full capture %s" % prof.get("capture")}
+def issue_ruler(kernel_key, sm_count, sm_hz):
+    """The integer roof of the tile kernels, as an executed-work ruler: they are bit manipulation, so what bounds them is the
+    rate at which the 4 schedulers of every SM can issue warp-instructions -- roof = SMs x 4 x clock.  Executed
+    instructions cannot be counted without a profiler, so instruction count AND duration both come from ONE ncu
+    capture (profiles/<kernel>_latest.json, written by profiles/collect_round.py), never a stored count over a live
+    time; the capture records the hash of the kernel sources and the block says when the sources have changed since.
+      issue_frac  = warp-instructions / duration / roof              (how busy the issue slots are with whatever issued)
+      useful_frac = issue_frac x (active threads per instruction / 32)   (lanes that did work)"""
+    if (C, R) != (10, 20):
+        return None                              # the captures are of the headline board
     try:
-        peak = json.load(open(os.path.join(ROOT, "profiles", "int_peak.json")))
-        thread_inst = prof["warp_instructions"] * prof["threads_per_instruction"]
-        out.update({"peak_alu_thread_ops_per_s": peak["alu_thread_ops_per_s"],
-                    "peak_source": "measured LOP3 throughput, 63.4 lanes/clk/SM (profiles/int_peak.json)",
-                    "thread_instructions_per_launch_all_pipes": thread_inst,
-                    "achieved_thread_instructions_per_s_all_pipes": thread_inst / (k1_ms * 1e-3)})
+        prof = json.load(open(os.path.join(ROOT, "profiles", "%s_latest.json" % kernel_key)))
     except Exception:
-        pass
+        return None
+    from tetris_b200 import _lib
+    roof = sm_count * 4 * sm_hz
+    rate = prof["warp_instructions"] / (prof["gpu_time_us"] * 1e-6)
+    out = {
+        "roof_warp_instructions_per_s": roof, "roof_source": "%d SMs x 4 schedulers x %.0f MHz" % (sm_count, sm_hz / 1e6),
+        "capture": prof.get("capture"), "capture_kernel": prof.get("kernel"), "capture_workload": prof.get("workload"),
+        "capture_stale": prof.get("source_hash") != _lib.source_hash(),
+        "warp_instructions_per_launch": prof["warp_instructions"], "capture_ms": prof["gpu_time_us"] * 1e-3,
+        "issue_frac": rate / roof, "active_threads_per_instruction": prof["threads_per_instruction"],
+        "useful_frac": rate / roof * prof["threads_per_instruction"] / 32.0,
+        "issue_active_pct_ncu": prof.get("issue_active_pct"), "alu_pipe_pct_ncu": prof.get("alu_pipe_pct"),
+        "xu_pipe_pct_ncu": prof.get("xu_pipe_pct"), "lsu_pipe_pct_ncu": prof.get("lsu_pipe_pct"),
+        "warps_active_pct_ncu": prof.get("warps_active_pct"), "registers_per_thread": prof.get("registers_per_thread"),
+        "shared_bank_conflict_frac": (prof["shared_bank_conflict_wavefronts"] / prof["shared_wavefronts"])
+        if prof.get("shared_wavefronts") else None,
+        "dram_bytes_per_launch_ncu": (prof.get("dram_bytes_read") or 0) + (prof.get("dram_bytes_write") or 0),
+    }
     return out
 
 
@@ -303,8 +321,11 @@ def run_ours(args):
     # together with the episode statistics -- the cycle of a caller that keeps its games on the host.  Copies, the two
     # conversion kernels and the final synchronisation are inside the timed region.  The env range is cut into chunks on
     # separate streams so the copies of one chunk overlap the rollout kernel of another.
+    if args.no_extras:
+        args.extras = "none"
+    light = args.extras == "light"
     e2e = e2e_serial = None
-    if not args.no_extras:
+    if args.extras == "full":
         from tetris_b200 import HostRollout
 
         def time_host_rollout(chunks):
@@ -337,7 +358,7 @@ def run_ours(args):
             e2e_serial = {"value": v1, "unit": "placements/s", "chunks": 1,
                           "note": "the same cycle as one chunk on one stream (no copy/compute overlap)"}
 
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and args.extras != "none":
         stats = env.stats_dict()
         out["rollout_afterstates_per_s_per_gpu"] = None
         # afterstates evaluated inside the timed rollouts (this rank): measured, not estimated
@@ -347,15 +368,24 @@ def run_ours(args):
         s.record(); env.rollout(T, "greedy", weights); e.record(); torch.cuda.synchronize()
         out["rollout_afterstates_per_s_per_gpu"] = (env.stats_dict()["afterstates"] - a0) / (s.elapsed_time(e) * 1e-3)
         out["episode_stats_rank0"] = {k: stats[k] for k in ("placements", "episodes", "lines", "max_ep_lines")}
-        # the timed step's own kernel (K3, k_rollout_greedy): its HBM traffic is only the env state in and out once per
-        # launch, so HBM says nothing about it -- it is K1's enumeration + features fused with the policy and the env
-        # step, bound by the integer pipes like K1 (whose roofline is reported below, as the north_star asks)
+        props = torch.cuda.get_device_properties(dev)
+        sm_hz = 1e6 * float((json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0))
+                            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1965.0)
+        peak, peak_src = measured_peak_gbs()
+        # ---- the timed step's own kernel (K3, k_rollout_greedy).  Its HBM traffic is the env state in and out once per
+        # launch of T placements, so the HBM fraction is tiny by construction; what bounds it is instruction issue (the
+        # work is K1's enumeration + features fused with the policy and the env step): see issue_ruler.
         k3_bytes = 2 * E * (STATE_READ_BYTES + 8)
-        out["step_kernel"] = {
-            "kernel": "k_rollout_greedy<%d,%d> (K3): %d placements per env per launch" % (C, R, T),
-            "algorithmic_bytes_per_launch": k3_bytes, "ms_per_launch": ms / K,
-            "hbm_gbs": k3_bytes / (ms / K * 1e-3) / 1e9,
-            "note": "not HBM-bound by construction (state stays on chip for the whole rollout); see roofline.integer_pipe",
+        k3_issue = issue_ruler("k3", props.multi_processor_count, sm_hz)
+        out["roofline_step_kernel"] = {
+            "kernel": "k_rollout_greedy<%d,%d> (K3): %d placements per env per launch, %d envs" % (C, R, T, E),
+            "bound": "issue slots (integer / bit work); HBM sees the env state once per launch",
+            "ms_per_launch": ms / K, "placements_per_s": E * T / (ms / K * 1e-3),
+            "afterstates_scored_per_s": out["rollout_afterstates_per_s_per_gpu"],
+            "hbm": {"achieved": k3_bytes / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": k3_bytes / (ms / K * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": k3_bytes,
+                    "traffic": (k3_issue or {}).get("dram_bytes_per_launch_ncu"), "peak_source": peak_src},
+            "issue": k3_issue,
         }
 
         # ---- roofline of the afterstate kernel (K1, the north_star's roofline target), timed live
@@ -378,124 +408,163 @@ def run_ours(args):
         rows_written = int(count.sum().item())                                      # legal ones: a 32 B feature row each
         # algorithmic bytes: state read + mask/count written + 32 B per legal afterstate
         alg_bytes = E * (STATE_READ_BYTES + 12) + 32 * rows_written
-        peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-        prof = {}
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "k1_latest.json")))
-        except Exception:
-            pass
+        k1_issue = issue_ruler("k1", props.multi_processor_count, sm_hz)
         out["roofline"] = {
             "kernel": "k_afterstates<%d,%d> (K1: enumerate + 8 features for every placement of %d envs)" % (C, R, E),
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": (prof.get("dram_bytes_read", 0) + prof.get("dram_bytes_write", 0)) or None,
-            "traffic_source": "ncu --set full capture %s (profiles/), dram__bytes_read+write per launch on the "
-                              "profiles/prof_run.py boards" % prof.get("capture") if prof else None,
+            "traffic": (k1_issue or {}).get("dram_bytes_per_launch_ncu"),
+            "traffic_source": "ncu --set full capture %s (profiles/k1_latest.json), dram__bytes_read+write per launch on the "
+                              "profiles/prof_run.py boards%s" % ((k1_issue or {}).get("capture"),
+                                                                 "; STALE: kernel sources changed since" if (k1_issue or {}).get("capture_stale") else ""),
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": k1_ms, "afterstates_per_s": slots_total / (k1_ms * 1e-3),
             "legal_afterstates_per_s": rows_written / (k1_ms * 1e-3),
-            "integer_pipe": integer_pipe(prof, k1_ms),
-            "note": "HBM is the lower roof on paper but the kernel is integer-ALU / latency bound (DESIGN.md section 4): "
-                    "frac is the HBM fraction, integer_pipe the measured pipe utilisation",
+            "issue": k1_issue,
+            "note": "HBM is the roof the contract asks for and the lower one on paper; the kernel is bound by instruction "
+                    "issue (DESIGN.md section 4): `frac` is the HBM fraction, `issue` the executed-work ruler",
         }
+        # the compact output format (int16 = 2 x feature): 16 B per legal afterstate
+        try:
+            feats16 = torch.empty((E, env.a_max, 8), dtype=torch.int16, device=dev)
+            for _ in range(2):
+                env.get_after_states(out=(feats16, valid, count), compact=True)
+            k1c = []
+            for _ in range(5):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); env.get_after_states(out=(feats16, valid, count), compact=True); e.record()
+                torch.cuda.synchronize()
+                k1c.append(s.elapsed_time(e))
+            k1c_ms = sum(k1c) / len(k1c)
+            algc = E * (STATE_READ_BYTES + 12) + 16 * rows_written
+            out["roofline"]["compact_i16"] = {"ms_per_launch": k1c_ms, "algorithmic_bytes_per_launch": algc,
+                                              "achieved": algc / (k1c_ms * 1e-3) / 1e9, "frac": algc / (k1c_ms * 1e-3) / 1e9 / peak}
+            del feats16
+        except Exception as ex:
+            out["roofline"]["compact_i16"] = {"error": repr(ex)}
+        # K2 (tb_step), timed live on the same boards
+        try:
+            a0 = torch.zeros(E, dtype=torch.int32, device=dev)
+            saved = env.state.clone()
+            env.step(a0, auto_reset=True, check=False)
+            k2 = []
+            for _ in range(5):
+                env.state.copy_(saved)
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); env.step(a0, auto_reset=True, check=False); e.record()
+                torch.cuda.synchronize()
+                k2.append(s.elapsed_time(e))
+            env.state.copy_(saved)
+            k2_ms = sum(k2) / len(k2)
+            k2_bytes = E * (2 * STATE_READ_BYTES + 4 + 4 + 1 + 4 + 32)
+            out["roofline_k2"] = {"kernel": "k_step<%d,%d> (K2)" % (C, R), "bound": "hbm", "ms_per_launch": k2_ms,
+                                  "algorithmic_bytes_per_launch": k2_bytes, "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9,
+                                  "peak": peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak,
+                                  "issue": issue_ruler("k2", props.multi_processor_count, sm_hz)}
+            del saved
+        except Exception as ex:
+            out["roofline_k2"] = {"error": repr(ex)}
         del feats
 
-        out["e2e"] = e2e
-        if e2e_serial is not None:
-            out["e2e_unpipelined"] = e2e_serial
-        host_stats = torch.empty(len(_lib.STATS), dtype=torch.int64).pin_memory()
-        # the same API with the games resident on the device (only weights in, statistics out)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            env.rollout(T, "greedy", np.array(BCTS_WEIGHTS, np.float32))
-            host_stats.copy_(env.stats, non_blocking=True)
+        if not light:
+            out["e2e"] = e2e
+            if e2e_serial is not None:
+                out["e2e_unpipelined"] = e2e_serial
+            host_stats = torch.empty(len(_lib.STATS), dtype=torch.int64).pin_memory()
+            # the same API with the games resident on the device (only weights in, statistics out)
             torch.cuda.synchronize()
-        out["e2e_resident"] = {"value": E * T * K / (time.perf_counter() - t0), "unit": "placements/s",
-                               "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 8 * len(_lib.STATS),
-                               "note": "BatchedTetris.rollout() with device-resident games: weights in, statistics out"}
+            t0 = time.perf_counter()
+            for _ in range(K):
+                env.rollout(T, "greedy", np.array(BCTS_WEIGHTS, np.float32))
+                host_stats.copy_(env.stats, non_blocking=True)
+                torch.cuda.synchronize()
+            out["e2e_resident"] = {"value": E * T * K / (time.perf_counter() - t0), "unit": "placements/s",
+                                   "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 8 * len(_lib.STATS),
+                                   "note": "BatchedTetris.rollout() with device-resident games: weights in, statistics out"}
 
-        # ---- e2e of the lockstep API a host-side policy uses: features to the host, actions back (PCIe-bound)
-        try:
-            nl = min(E, 1 << 18)
-            env2 = BatchedTetris(C, R, nl, piece_set=PIECE_SET, seed=args.seed + 1, device=dev)
-            env2.rollout(20, "random")
-            hc = torch.empty(nl, dtype=torch.int32).pin_memory()
-            ha = torch.zeros(nl, dtype=torch.int32).pin_memory()
-            ho = torch.empty((nl, 8), dtype=torch.float32).pin_memory()
-            n_it = 3
-            for compact in (False, True):                              # float32 rows, then the int16 (2 x feature) rows
-                hf = torch.empty((nl, env2.a_max, 8), dtype=torch.int16 if compact else torch.float32).pin_memory()
-                df = torch.empty((nl, env2.a_max, 8), dtype=hf.dtype, device=dev)
-                dv = torch.empty(nl, dtype=torch.int64, device=dev)
-                dc = torch.empty(nl, dtype=torch.int32, device=dev)
-                for it in range(n_it + 1):                             # first iteration = warm-up (pinned pages, caches)
-                    if it == 1:
+            # ---- e2e of the lockstep API a host-side policy uses: features to the host, actions back (PCIe-bound)
+            try:
+                nl = min(E, 1 << 18)
+                env2 = BatchedTetris(C, R, nl, piece_set=PIECE_SET, seed=args.seed + 1, device=dev)
+                env2.rollout(20, "random")
+                hc = torch.empty(nl, dtype=torch.int32).pin_memory()
+                ha = torch.zeros(nl, dtype=torch.int32).pin_memory()
+                ho = torch.empty((nl, 8), dtype=torch.float32).pin_memory()
+                n_it = 3
+                for compact in (False, True):                              # float32 rows, then the int16 (2 x feature) rows
+                    hf = torch.empty((nl, env2.a_max, 8), dtype=torch.int16 if compact else torch.float32).pin_memory()
+                    df = torch.empty((nl, env2.a_max, 8), dtype=hf.dtype, device=dev)
+                    dv = torch.empty(nl, dtype=torch.int64, device=dev)
+                    dc = torch.empty(nl, dtype=torch.int32, device=dev)
+                    for it in range(n_it + 1):                             # first iteration = warm-up (pinned pages, caches)
+                        if it == 1:
+                            torch.cuda.synchronize()
+                            t0 = time.perf_counter()
+                        f, v, c = env2.get_after_states(out=(df, dv, dc), compact=compact)
+                        hf.copy_(f, non_blocking=True); hc.copy_(c, non_blocking=True)
                         torch.cuda.synchronize()
-                        t0 = time.perf_counter()
-                    f, v, c = env2.get_after_states(out=(df, dv, dc), compact=compact)
-                    hf.copy_(f, non_blocking=True); hc.copy_(c, non_blocking=True)
-                    torch.cuda.synchronize()
-                    obs, rew, done, lines = env2.step(ha.to(dev, non_blocking=True), auto_reset=True, check=False)
-                    ho.copy_(obs, non_blocking=True)
-                    torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                out["e2e_lockstep_host_policy" + ("_compact" if compact else "")] = {
-                    "value": nl * n_it / dt, "unit": "placements/s", "envs": nl,
-                    "h2d_bytes_per_step": 4 * nl, "d2h_bytes_per_step": nl * (env2.a_max * (16 if compact else 32) + 4 + 32),
-                    "note": "get_after_states -> features D2H -> actions H2D -> step -> obs D2H (action 0 for all envs)"
-                            + ("; features as int16 = 2 x feature (TB_FLAG_FEATS_I16)" if compact else "")}
-                del hf, df
-            del env2
-        except Exception as ex:                                        # side measurement only
-            out["e2e_lockstep_host_policy"] = {"error": repr(ex)}
+                        obs, rew, done, lines = env2.step(ha.to(dev, non_blocking=True), auto_reset=True, check=False)
+                        ho.copy_(obs, non_blocking=True)
+                        torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    out["e2e_lockstep_host_policy" + ("_compact" if compact else "")] = {
+                        "value": nl * n_it / dt, "unit": "placements/s", "envs": nl,
+                        "h2d_bytes_per_step": 4 * nl, "d2h_bytes_per_step": nl * (env2.a_max * (16 if compact else 32) + 4 + 32),
+                        "note": "get_after_states -> features D2H -> actions H2D -> step -> obs D2H (action 0 for all envs)"
+                                + ("; features as int16 = 2 x feature (TB_FLAG_FEATS_I16)" if compact else "")}
+                    del hf, df
+                del env2
+            except Exception as ex:                                        # side measurement only
+                out["e2e_lockstep_host_policy"] = {"error": repr(ex)}
 
-        # ---- random policy and the 4096-env lockstep config, for context
-        try:
-            envr = BatchedTetris(C, R, E, piece_set=PIECE_SET, seed=args.seed + 2, device=dev)
-            envr.rollout(30, "random")
-            torch.cuda.synchronize()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(); envr.rollout(64, "random"); e.record(); torch.cuda.synchronize()
-            out["random_policy_placements_per_s_per_gpu"] = E * 64 / (s.elapsed_time(e) * 1e-3)
-            del envr
-            env4 = BatchedTetris(C, R, 4096, piece_set=PIECE_SET, seed=args.seed, device=dev)
-            g = torch.Generator(device=dev); g.manual_seed(0)
-            for it in range(60):
-                if it == 10:
-                    torch.cuda.synchronize(); t0 = time.perf_counter()
-                f, v, c = env4.get_after_states()
-                a = (torch.randint(0, 2 ** 31 - 1, (4096,), device=dev, generator=g) % c.long()).int()
-                env4.step(a, auto_reset=True, check=False)
-            torch.cuda.synchronize()
-            out["lockstep_4096_placements_per_s"] = 4096 * 50 / (time.perf_counter() - t0)
-            # the same iteration captured once in a CUDA graph (launch-bound at this batch size)
-            envg = BatchedTetris(C, R, 4096, piece_set=PIECE_SET, seed=args.seed, device=dev)
-            replay, _outs = envg.capture_lockstep(           # default CUDA generator: graph-safe philox offsets
-                lambda f, v, c: (torch.randint(0, 2 ** 31 - 1, (4096,), device=dev) % c.long().clamp(min=1)).int())
-            for _ in range(10):
-                replay()
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            for _ in range(200):
-                replay()
-            torch.cuda.synchronize()
-            out["lockstep_4096_cuda_graph_placements_per_s"] = 4096 * 200 / (time.perf_counter() - t0)
-            # the same 4096 envs with the policy inside the kernel (fused rollouts, small-batch tile configuration)
-            for pol in ("random", "greedy"):
-                envg.rollout(64, pol)
+            # ---- random policy and the 4096-env lockstep config, for context
+            try:
+                envr = BatchedTetris(C, R, E, piece_set=PIECE_SET, seed=args.seed + 2, device=dev)
+                envr.rollout(30, "random")
                 torch.cuda.synchronize()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record(); envg.rollout(256, pol); e.record(); torch.cuda.synchronize()
-                out["fused_4096_%s_placements_per_s" % pol] = 4096 * 256 / (s.elapsed_time(e) * 1e-3)
-        except Exception as ex:
-            out["random_policy_placements_per_s_per_gpu"] = repr(ex)
+                s.record(); envr.rollout(64, "random"); e.record(); torch.cuda.synchronize()
+                out["random_policy_placements_per_s_per_gpu"] = E * 64 / (s.elapsed_time(e) * 1e-3)
+                del envr
+                env4 = BatchedTetris(C, R, 4096, piece_set=PIECE_SET, seed=args.seed, device=dev)
+                g = torch.Generator(device=dev); g.manual_seed(0)
+                for it in range(60):
+                    if it == 10:
+                        torch.cuda.synchronize(); t0 = time.perf_counter()
+                    f, v, c = env4.get_after_states()
+                    a = (torch.randint(0, 2 ** 31 - 1, (4096,), device=dev, generator=g) % c.long()).int()
+                    env4.step(a, auto_reset=True, check=False)
+                torch.cuda.synchronize()
+                out["lockstep_4096_placements_per_s"] = 4096 * 50 / (time.perf_counter() - t0)
+                # the same iteration captured once in a CUDA graph (launch-bound at this batch size)
+                envg = BatchedTetris(C, R, 4096, piece_set=PIECE_SET, seed=args.seed, device=dev)
+                replay, _outs = envg.capture_lockstep(           # default CUDA generator: graph-safe philox offsets
+                    lambda f, v, c: (torch.randint(0, 2 ** 31 - 1, (4096,), device=dev) % c.long().clamp(min=1)).int())
+                for _ in range(10):
+                    replay()
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                for _ in range(200):
+                    replay()
+                torch.cuda.synchronize()
+                out["lockstep_4096_cuda_graph_placements_per_s"] = 4096 * 200 / (time.perf_counter() - t0)
+                # the same 4096 envs with the policy inside the kernel (fused rollouts, small-batch tile configuration)
+                for pol in ("random", "greedy"):
+                    envg.rollout(64, pol)
+                    torch.cuda.synchronize()
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(); envg.rollout(256, pol); e.record(); torch.cuda.synchronize()
+                    out["fused_4096_%s_placements_per_s" % pol] = 4096 * 256 / (s.elapsed_time(e) * 1e-3)
+            except Exception as ex:
+                out["random_policy_placements_per_s_per_gpu"] = repr(ex)
 
-        # ---- CPU baseline beside it (N = 1 only): the oracle port on this box's host cores
-        if world == 1:
-            threads = os.cpu_count() or 1
-            v, av, sample = cpu_port_rate(12.0, threads)
-            out["cpu_baseline"] = {"value": v, "unit": "placements/s", "cores": threads, "kind": "port",
-                                   "sample": sample, "afterstates_per_s": av, "python_reference": PYTHON_REFERENCE}
+            # ---- CPU baseline beside it (N = 1 only): the oracle port on this box's host cores
+            if world == 1:
+                threads = os.cpu_count() or 1
+                v, av, sample = cpu_port_rate(12.0, threads)
+                out["cpu_baseline"] = {"value": v, "unit": "placements/s", "cores": threads, "kind": "port",
+                                       "sample": sample, "afterstates_per_s": av, "python_reference": PYTHON_REFERENCE}
 
     if rank == 0:
         print(json.dumps(out))

@@ -11,7 +11,7 @@ cap() {  # name, kernel regex, skip, mangled-name substring for the line tools
 }
 for k in "$@"; do
   case $k in
-    k1) cap k1 k_afterstates 1 k_afterstatesILi10ELi20ELb0ELi256ELi3ELi256E ;;
+    k1) cap k1 k_afterstates 1 k_afterstatesILi10ELi20ELi0ELi256ELi3ELi256E ;;
     k3) cap k3 k_rollout_greedy 2 k_rollout_greedyILi10ELi20ELi256ELi3ELi256E ;;
     k2) cap k2 k_step 1 k_stepILi10ELi20ELi256ELi4E ;;
     k3r) cap k3r k_rollout_random 1 k_rollout_randomILi10ELi20EE ;;

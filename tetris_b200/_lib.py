@@ -44,6 +44,16 @@ def _stale():
     return _newer(SOURCES, SO_PATH)
 
 
+def source_hash():
+    """sha256 (first 16 hex digits) over the kernel sources: profiles/<kernel>_latest.json records the value its ncu capture
+    was taken from, and bench.py flags quoted capture figures as stale when the sources have changed since."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("tb_core.cuh", "tb_kernels.cuh", "tb_shape.h"):
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _nvcc():
     return os.environ.get("NVCC") or "nvcc"
 

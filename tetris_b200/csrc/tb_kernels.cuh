@@ -212,7 +212,6 @@ struct CtaSmem {
                                          //           K3: best orderable score per column loop
     uint32_t sloc[TILE][2];              // by slot: placements that need the general evaluation (they clear a line),
                                          // per column loop, same bit layout as vloc in K1 (16 bits per orientation)
-    alignas(16) uint32_t run[RunTab<R>::SIZE];
     uint16_t slot_of[TILE];              // env (thread of the tile) -> slot; kNoSlot: the env takes no part
     uint16_t sprefix[TILE];              // K1 phase S: inclusive count of slow items over the slots of each 32-slot group
     int wtot[TILE / 32];                 //             and the groups' totals
@@ -237,8 +236,10 @@ template <int TILE, int THREADS = TILE> struct BestSmem {
 static __device__ const OdescImage g_odesc = make_odesc_image();
 template <int R> static __device__ const RunImage<R> g_run = make_run_image<R>();
 
+// s_run: the run-sum table, in STATIC shared memory (its address is then an immediate of every lookup; inside the
+// dynamic block each of the ~9 lookups per afterstate paid an add of the block's base)
 template <int C, int R, int TILE>
-__device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
+__device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm, uint32_t *s_run)
 {
     if (threadIdx.x < kNumOris) sm.ori[threadIdx.x] = c_ori[threadIdx.x];
     {
@@ -260,10 +261,10 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm)
     if (threadIdx.x <= kNumPieces) { sm.cnt[0][threadIdx.x] = 0; sm.cnt[1][threadIdx.x] = 0; }
     if (RunTab<R>::SIZE % 4 == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_run<R>.v);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm.run);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_run);
         for (int i = threadIdx.x; i < RunTab<R>::SIZE / 4; i += blockDim.x) dst[i] = src[i];
     } else {
-        for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) sm.run[m] = g_run<R>.v[m];
+        for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) s_run[m] = g_run<R>.v[m];
     }
     __syncthreads();
 }
@@ -404,7 +405,8 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     static_assert(TILE % 32 == 0 && THREADS % TILE == 0, "TILE: whole warps of envs; THREADS: a multiple of TILE");
     constexpr int NWARPS = THREADS / 32, NGROUPS = TILE / 32;
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
-    stage_cta(sm);
+    __shared__ __align__(16) uint32_t s_run[RunTab<R>::SIZE];
+    stage_cta(sm, s_run);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool env_thread = THREADS == TILE || tid < TILE;   // this thread owns env `tid` of the tile in the per-env phases
     const bool want_terminal = (flags & TB_FLAG_INCLUDE_TERMINAL) != 0;
@@ -432,7 +434,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
             uint32_t *myrec = sm.rec + myslot * K::WORDS;
 #pragma unroll
             for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
-            build_env<C, R>(sm.run, myrec);
+            build_env<C, R>(s_run, myrec);
             sm.env_of[myslot] = (uint8_t)tid;
             sm.pid[myslot] = (uint8_t)piece;
             sm.vloc[myslot][0] = 0u; sm.vloc[myslot][1] = 0u;
@@ -473,7 +475,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                     bool slow = false, legal = false;
                     if (on) {
                         Eval ev;
-                        const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
+                        const int status = eval_neigh<C, R, W>(rec, s_run, nb, u, c, ev);
                         if (status == kFastDone) { if (aslot < a_stride) emit_row<FMT>(feat_row<FMT>(feats, env, a_stride, aslot), ev, dirs); }
                         else if (status == kFastClears) slow = (!ev.terminal || want_terminal) && aslot < a_stride;
                         else slow = want_terminal && aslot < a_stride;
@@ -552,7 +554,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 // terminal afterstates (only evaluated with TB_FLAG_INCLUDE_TERMINAL) need the general wells code; without
                 // the flag every item is a legal placement and the table form applies (kernel-uniform choice)
                 eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr,
-                                want_terminal ? nullptr : sm.run);
+                                want_terminal ? nullptr : s_run);
                 emit_row<FMT>(feat_row<FMT>(feats, e0 + (int64_t)sm.env_of[oslot], a_stride, aslot), ev, dirs);
             }
         }
@@ -719,7 +721,7 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
                 int ori, c;
                 slot_to_placement(pw, C, sel, ori, c);
                 Eval ev;
-                eval_slow<C, R>(col, sm.ori[ori], c, ev, col, sm.run);        // current_state = afterstates[action]
+                eval_slow<C, R>(col, sm.ori[ori], c, ev, col, sm.run);       // current_state = afterstates[action]
                 lc = popc32(ev.full);                                         // game.py:85
                 if (obs) {                                                    // game.py:91 (stored here: fewer live registers)
                     float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
@@ -982,7 +984,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
     BestSmem<TILE, THREADS> &bs =
         *reinterpret_cast<BestSmem<TILE, THREADS> *>(smem_raw + ((sizeof(CtaSmem<C, R, TILE>) + 15) & ~(size_t)15));
-    stage_cta(sm);
+    __shared__ __align__(16) uint32_t s_run[RunTab<R>::SIZE];
+    stage_cta(sm, s_run);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool env_thread = THREADS == TILE || tid < TILE;   // this thread owns env `tid` of the tile in the per-env phases
     const int64_t n_tiles = (sv.n_env + TILE - 1) / TILE;
@@ -1020,7 +1023,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 uint32_t *myrec = sm.rec + myslot * K::WORDS;
 #pragma unroll
                 for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
-                build_env<C, R>(sm.run, myrec);
+                build_env<C, R>(s_run, myrec);
                 sm.pid[myslot] = (uint8_t)mt.piece;
                 sm.vloc[myslot][0] = 0u; sm.vloc[myslot][1] = 0u;
                 sm.sloc[myslot][0] = 0u; sm.sloc[myslot][1] = 0u;
@@ -1060,7 +1063,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                         bool slow = false;
                         if (on) {
                             Eval ev;
-                            const int status = eval_neigh<C, R, W>(rec, sm.run, nb, u, c, ev);
+                            const int status = eval_neigh<C, R, W>(rec, s_run, nb, u, c, ev);
                             if (status == kFastDone) {
                                 const uint32_t ord = orderable(fitness(ev.f, wts.v));         // game.py:109-120
                                 if (ord > best_ord) { best_ord = ord; best_slot = aslot; }    // slots ascend with o
@@ -1114,7 +1117,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                 const int aslot = l ? n0 * (C - w0 + 1) + cc * n1 + o : cc * n0 + o;
                 Eval ev;
                 eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr,
-                                sm.run);                   // legal placements only: non-terminal, wells by table
+                                s_run);                   // legal placements only: non-terminal, wells by table
                 atomicMax(&bs.best[oslot], score_key(orderable(fitness(ev.f, wts.v)), aslot));
             });
             if (WPG == 1) __syncwarp();                    // phase C reads the best keys of this warp's envs only
@@ -1435,7 +1438,8 @@ struct ShapeOps {
         // k2_cfg (tuning): 0 = 256 envs x 4 CTAs per SM (default), 1 = 128 x 8, 2 = 256 x 3
         const F8 one = f8_from(nullptr, 1.0f);
         cudaStream_t st = (cudaStream_t)cx->stream;
-        if (cx->k2_cfg == 1)
+        // small batches (fewer 256-env tiles than SMs): 128-env CTAs, twice as many SMs busy
+        if (cx->k2_cfg == 1 || (cx->k2_cfg < 0 && (n_env + 255) / 256 < cx->sm_count))
             k_step<C, R, 128, 8><<<(unsigned)((n_env + 127) / 128), 128, 0, st>>>(
                 view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
         else if (cx->k2_cfg == 2)
