@@ -244,7 +244,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")                          # a caller's (the driver's) setting is kept
+        # NCCL_DEBUG is the caller's (the driver reads the communicator lines); its output goes to stderr unless the
+        # caller says otherwise, because stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     K, W, T, E = args.steps, args.warmup, args.rollout_steps, args.envs
     W = max(W, 3)

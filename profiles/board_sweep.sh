@@ -11,6 +11,8 @@ done
 python - $out <<'PY'
 import json, sys
 for ln in open(sys.argv[1]):
+    if not ln.startswith("{"):
+        continue
     d = json.loads(ln)
     r, k3 = d.get("roofline", {}), d.get("roofline_step_kernel", {})
     print("%-6s N=%d  %.3e placements/s  %.2f ms/step | K1 %.3f ms, HBM frac %.3f | K3 %.3e afterstates/s" % (
