@@ -25,6 +25,16 @@
 #define TB_HD inline
 #endif
 
+// Bounds / precondition checks of the kernels: compiled in with -DTB_DEBUG_CHECKS (device-side assert -> the launch
+// fails with "device-side assert triggered"), compiled out otherwise.  compute-sanitizer is not available on the GPU
+// pool, so the parity suite is run once per round against a library built with the checks (profiles/README.md).
+#if defined(TB_DEBUG_CHECKS)
+#include <assert.h>
+#define TB_CHECK(cond) assert(cond)
+#else
+#define TB_CHECK(cond) ((void)0)
+#endif
+
 namespace tb {
 
 // ---------------------------------------------------------------------------------------------
@@ -219,6 +229,7 @@ TB_HD int bag_draw(int n_set, uint64_t key, uint32_t &bag, uint32_t &draws)
     draws += 1;
     uint32_t b = bag;
     for (uint32_t i = 0; i < j; ++i) b &= b - 1;
+    TB_CHECK(b != 0u);
     const int idx = ctz32(b);
     bag &= ~(1u << idx);
     return idx;
@@ -508,6 +519,7 @@ TB_HD uint32_t run_sum_acc(const uint32_t *tab, uint32_t w, uint32_t acc)
 {
     constexpr int HB = RunTab<R>::HB, NCH = RunTab<R>::NCH;
     constexpr uint32_t M = (uint32_t)(RunTab<R>::SIZE - 1);
+    TB_CHECK((NCH * HB >= 32) || (w >> (NCH * HB)) == 0u);         // a well mask of a non-terminal board: below row R
     if (NCH == 1) return acc + (tab[w] & 255u);
     const uint32_t e0 = tab[w & M], e1 = tab[(w >> HB) & M];
     // e1 permuted to bytes [1, trail1, 0, rs1] against e0 = [rs0, lead0, trail0, 1]

@@ -86,10 +86,19 @@ __device__ __forceinline__ uint4 pack_meta(const uint32_t *col, Meta mt)
     }
     return make_uint4(w[0], w[1], w[2] | ((uint32_t)mt.piece << 16) | (mt.bag << 24), mt.draws);
 }
+template <int C>
+__device__ __forceinline__ int max_height_raw(const uint32_t *col)
+{
+    uint32_t any = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) any |= col[c];
+    return height_of(any);
+}
 template <int C, int R>
 __device__ __forceinline__ void load_board(const StateView &sv, int64_t e, uint32_t *col)
 {
     using S = Shape<C, R>;
+    TB_CHECK(e >= 0 && e < sv.n_env);
     uint32_t w[S::NW];
 #pragma unroll
     for (int b = 0; b < S::NB; ++b) {
@@ -97,11 +106,13 @@ __device__ __forceinline__ void load_board(const StateView &sv, int64_t e, uint3
         w[4 * b] = v.x; w[4 * b + 1] = v.y; w[4 * b + 2] = v.z; w[4 * b + 3] = v.w;
     }
     rows_to_cols<C, R>(w, col);
+    TB_CHECK(max_height_raw<C>(col) <= S::N);
 }
 template <int C, int R>
 __device__ __forceinline__ void store_board(const StateView &sv, int64_t e, const uint32_t *col)
 {
     using S = Shape<C, R>;
+    TB_CHECK(e >= 0 && e < sv.n_env);
     uint32_t w[S::NW];
     cols_to_rows<C, R>(col, w);
 #pragma unroll
@@ -148,6 +159,7 @@ __device__ __forceinline__ bool any_valid(const uint32_t *col, uint32_t pw, cons
 // position of the n-th (0-based) set bit of m; n < popc(m)
 __device__ __forceinline__ int nth_set_bit(unsigned long long m, int n)
 {
+    TB_CHECK(n >= 0 && n < __popcll(m));
     const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
     const int plo = __popc(lo);
     const bool low = n < plo;
@@ -429,8 +441,10 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
         int myslot = kNoSlot;
         if (piece < kNumPieces) {
             myslot = slot_from_rank(cnt, piece, rank);
+            TB_CHECK(myslot >= 0 && myslot < TILE && rank < cnt[piece]);
             uint32_t col[C];
             load_board<C, R>(sv, e, col);
+            TB_CHECK(max_height_raw<C>(col) <= R);         // the record's precondition: a non-terminal board
             uint32_t *myrec = sm.rec + myslot * K::WORDS;
 #pragma unroll
             for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
@@ -462,8 +476,10 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 const int idx = lane_ok ? window_position<EPW, D>(win, k, np) : idx0;
                 const bool on = lane_ok && idx < np;
                 const int slot = pbase + (on ? idx : idx0);
+                TB_CHECK(idx0 >= 0 && idx0 < np && slot >= 0 && slot < TILE && pbase + np <= TILE);
                 const uint32_t *rec = sm.rec + slot * K::WORDS;
                 const int64_t env = e0 + (int64_t)sm.env_of[slot];
+                TB_CHECK(env < sv.n_env && (int)sm.pid[slot] == (int)(jb & 15u));
                 Neigh<C, R, W> nb;
                 load_neigh<C, R, W>(rec, c, nb);
                 uint32_t vsel = 0u, ssel = 0u;              // leader lane: legal / slow columns of its env, 16 bits per orientation
@@ -542,10 +558,12 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 for (int step = 16; step; step >>= 1)
                     if ((int)pre[owner + step - 1] <= li) owner += step;
                 const int oslot = (g << 5) + owner;
+                TB_CHECK(g < NGROUPS && owner < 32 && oslot < n_active && (int)pre[owner] > li);
                 const uint32_t om0 = sm.sloc[oslot][0], om1 = sm.sloc[oslot][1];
                 const int r = li - ((int)pre[owner] - __popc(om0) - __popc(om1)), p0 = __popc(om0);
                 const int l = r >= p0;
                 const int bit = (int)__fns(l ? om1 : om0, 0u, (l ? r - p0 : r) + 1);
+                TB_CHECK(bit >= 0 && bit < 32);
                 const int o = bit >> 4, cc = bit & 15;
                 const uint32_t pw = sm.piece[sm.pid[oslot]];
                 const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
@@ -555,6 +573,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 // the flag every item is a legal placement and the table form applies (kernel-uniform choice)
                 eval_slow<C, R>(sm.rec + oslot * K::WORDS + K::COLX + 2, sm.ori[obase + (l ? n0 : 0) + o], cc, ev, nullptr,
                                 want_terminal ? nullptr : s_run);
+                TB_CHECK(aslot < a_stride && e0 + (int64_t)sm.env_of[oslot] < sv.n_env);
                 emit_row<FMT>(feat_row<FMT>(feats, e0 + (int64_t)sm.env_of[oslot], a_stride, aslot), ev, dirs);
             }
         }
@@ -737,7 +756,9 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
 #pragma unroll
             for (int k = 0; k < C; ++k) sm.cols[tid][k] = col[k];
             sm.lpiece[tid] = (uint8_t)mt.piece;
-            sm.list[atomicAdd(&sm.n_list[pass], 1)] = (uint16_t)tid;
+            const int li = atomicAdd(&sm.n_list[pass], 1);
+            TB_CHECK(li >= 0 && li < TILE);
+            sm.list[li] = (uint16_t)tid;
         }
         __syncthreads();
         // ---- pooled: legal slots of the listed envs (game.py:69 / :94-100), one thread per list entry.  (A warp per entry
@@ -745,6 +766,7 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
         // 0.148 ms against 0.122 ms per 2^20 envs, profiles/README.md r2f.)
         if (tid < sm.n_list[pass]) {
             const int env = (int)sm.list[tid];
+            TB_CHECK(env >= 0 && env < TILE && sm.lpiece[env] < kNumPieces);
             uint32_t c2[C];
 #pragma unroll
             for (int k = 0; k < C; ++k) c2[k] = sm.cols[env][k];
@@ -1020,6 +1042,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             int myslot = kNoSlot, n_slots = 0;
             if (active) {
                 myslot = slot_from_rank(cnt, mt.piece, rank);
+                TB_CHECK(myslot >= 0 && myslot < TILE && rank < cnt[mt.piece]);
+                TB_CHECK(max_height_raw<C>(col) <= R);     // the record's precondition: a non-terminal board
                 uint32_t *myrec = sm.rec + myslot * K::WORDS;
 #pragma unroll
                 for (int i = 0; i < C; ++i) myrec[K::COLX + 2 + i] = col[i];
@@ -1049,6 +1073,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     const int idx = lane_ok ? window_position<EPW, D>(win, k, np) : idx0;
                     const bool on = lane_ok && idx < np;
                     const int slot = pbase + (on ? idx : idx0);
+                    TB_CHECK(idx0 >= 0 && idx0 < np && slot >= 0 && slot < TILE && pbase + np <= TILE);
+                    TB_CHECK((int)sm.pid[slot] == (int)(jb & 15u));
                     const uint32_t *rec = sm.rec + slot * K::WORDS;
                     Neigh<C, R, W> nb;
                     load_neigh<C, R, W>(rec, c, nb);
