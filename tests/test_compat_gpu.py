@@ -294,3 +294,18 @@ def test_example_play_flow():
         assert example_play.main(100, quiet=True, seed=0) == -71
     finally:
         sys.path.remove(d)
+
+
+def test_state_rejects_inconsistent_heights():
+    """State(representation, lowest_free_rows=...) (state.py:22-25): heights that match the board are accepted (what
+    every reference call site passes), heights that do not are rejected instead of silently ignored."""
+    from tetris import state
+    rep = np.zeros((14, 10), np.int64)
+    rep[:3, 2] = 1
+    rep[0, 5] = 1
+    h = np.zeros(10, np.int64); h[2] = 3; h[5] = 1
+    s = state.State(rep, lowest_free_rows=h)
+    assert np.array_equal(s.lowest_free_rows, h)
+    bad = h.copy(); bad[5] = 2
+    with pytest.raises(ValueError, match="lowest_free_rows"):
+        state.State(rep, lowest_free_rows=bad)

@@ -31,6 +31,16 @@ class State:
         for k in range(min(len(ppcr), len(changed))):
             packed |= (int(ppcr[k]) & 15) << (4 * k)
         n_rows, n_cols = rep.shape
+        if lowest_free_rows is not None:
+            # The reference trusts the caller's heights (state.py:22-25) for hard drop, line clear and features; the
+            # kernels derive them from the board.  Every reference call site passes heights that match the board, so a
+            # mismatch is rejected loudly rather than silently ignored.
+            given = np.asarray(lowest_free_rows).astype(np.int64).ravel()
+            filled = rep != 0
+            want = np.where(filled.any(axis=0), n_rows - np.argmax(filled[::-1], axis=0), 0)
+            if given.shape != want.shape or np.any(given != want):
+                raise ValueError("lowest_free_rows does not match the representation (expected %s); pass None to have "
+                                 "it computed (state.py:162-172)" % want.tolist())
         c = _single.ctx(n_cols, n_rows - 4)
         rows, heights, n_cleared, full_mask, terminal, feats = c.eval_state(
             _single.pack_rows(rep), int(changed[0]), len(changed), packed, bonus2)
