@@ -84,13 +84,19 @@ saved_r = envr.state.clone()
 for cfg in [int(x) for x in a.k2.split(",") if x != ""]:
     if not tune("k2_cfg", cfg) and cfg != 0:
         continue
-    env.state.copy_(saved)
-    for _ in range(2):
-        env.step(a0, auto_reset=True, check=False)
-    env.state.copy_(saved)
-    out["k2_cfg%d_ms" % cfg] = timed(lambda: env.step(a0, auto_reset=True, check=False), 5)
-    envr.state.copy_(saved_r)                # tall boards (random play): many envs need the legality test
-    out["k2_cfg%d_tall_ms" % cfg] = timed(lambda: envr.step(a0, auto_reset=True, check=False), 5)
+    for name, ev, sv_ in (("", env, saved), ("_tall", envr, saved_r)):   # greedy-play boards; tall (random-play) boards
+        ts = []
+        for rep in range(7):
+            ev.state.copy_(sv_)                  # the same boards every repetition (a step changes them)
+            flush.zero_()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record(); ev.step(a0, auto_reset=True, check=False); e_.record()
+            torch.cuda.synchronize()
+            if rep >= 2:
+                ts.append(s_.elapsed_time(e_))
+        ts.sort()
+        out["k2_cfg%d%s_ms" % (cfg, name)] = ts[len(ts) // 2]
+    envr.state.copy_(saved_r)
 tune("k2_cfg", -1)
 for cfg in [int(x) for x in a.k3r.split(",") if x != ""]:
     if not tune("k3r_cfg", cfg) and cfg != 0:

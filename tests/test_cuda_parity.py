@@ -740,3 +740,37 @@ def test_render_any_env_and_wide_board(capsys):
         if done:
             g.reset()
     assert g.current_state.representation.shape == (13, 7)
+
+
+@pytest.mark.parametrize("k2cfg", [0, 1, 2])
+def test_step_kernel_configurations(k2cfg):
+    """tb_step picks its CTA shape by batch size (256 envs x 4 CTAs per SM; 128 x 8 for small batches); every shape must
+    give the oracle's results.  Forced through the tuning hook on boards where many envs are within 4 rows of the top
+    (the pooled legality test has work) and game overs are frequent; plus one batch big enough to take the default
+    path without the hook."""
+    from oracle import oracle as orc
+    from tetris_b200 import BatchedTetris, _lib
+    _lib.set_tuning("k2_cfg", k2cfg)
+    try:
+        cases = [(6, 12, 3001, 30), (10, 20, 1500, 40)] + ([(10, 10, 40000, 12)] if k2cfg == 0 else [])
+        for (Cc, R, n, steps) in cases:
+            if n == 40000:
+                _lib.set_tuning("k2_cfg", -1)
+            env = BatchedTetris(Cc, R, n, piece_set=1, seed=19)
+            ob = orc.Batch(Cc, R, n, piece_set=1, seed=19)
+            ob.reset()
+            env.rollout(20, "random"); ob.rollout(20, 0, threads=8)
+            u = np.random.RandomState(3).randint(0, 2 ** 31 - 1, size=(steps, n))
+            n_done = 0
+            for t in range(steps):
+                _f, _v, count = env.get_after_states()
+                a = (u[t] % count.cpu().numpy()).astype(np.int32)
+                obs, rew, done, lines = env.step(a, auto_reset=True)
+                oobs, orew, odone, olines = ob.step(a, auto_reset=True)
+                assert np.array_equal(obs.cpu().numpy(), oobs) and np.array_equal(rew.cpu().numpy(), orew), (Cc, R, t)
+                assert np.array_equal(done.cpu().numpy(), odone) and np.array_equal(lines.cpu().numpy(), olines), (Cc, R, t)
+                n_done += int(odone.sum())
+            _compare_state(env, ob)
+            assert n_done > 0
+    finally:
+        _lib.set_tuning("k2_cfg", -1)

@@ -671,6 +671,7 @@ struct StepSmem {
     uint32_t ori[32], piece[16];
 };
 
+// named barriers (ids 1..15; 0 is __syncthreads): arrive = signal without waiting
 template <int C, int R, int TILE, int MINB>
 __global__ void __launch_bounds__(TILE, MINB)
 k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int32_t *__restrict__ actions,
@@ -761,9 +762,10 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
             sm.list[li] = (uint16_t)tid;
         }
         __syncthreads();
-        // ---- pooled: legal slots of the listed envs (game.py:69 / :94-100), one thread per list entry.  (A warp per entry
-        // with lane = enumeration slot shortens the wait at the barrier but issues more instructions in total:
-        // 0.148 ms against 0.122 ms per 2^20 envs, profiles/README.md r2f.)
+        // ---- pooled: legal slots of the listed envs (game.py:69 / :94-100), one thread per list entry.  (Measured and
+        // rejected, profiles/README.md r2f / r2l: a warp per entry with lane = enumeration slot -- shorter wait at the
+        // barrier, more instructions in total, 0.148 vs 0.122 ms; split barriers where only the consumer warps and the
+        // warps that listed an env wait (bar.arrive for the rest) -- 0.089 vs 0.085 ms.)
         if (tid < sm.n_list[pass]) {
             const int env = (int)sm.list[tid];
             TB_CHECK(env >= 0 && env < TILE && sm.lpiece[env] < kNumPieces);
@@ -785,6 +787,84 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
 #pragma unroll
         for (int k = 0; k < C; ++k) col[k] = 0u;
         mt.piece = draw_piece(piece_set, env_key(seed, (uint64_t)(env_offset + e)), mt, nullptr, e);
+        ep = make_uint2(0u, 0u);
+    }
+    store_board<C, R>(sv, e, col);
+    sv.meta[e] = pack_meta<C>(col, mt);
+    sv.epi[e] = ep;
+}
+
+// K2, thread per env without CTA-level cooperation (round 1's structure, plus the table-based evaluation of the chosen
+// afterstate): no barriers after the table staging, two inlined copies of the legality test.  Kept as tuning
+// configuration k2_cfg = 5 for A/B runs.
+template <int C, int R>
+__global__ void __launch_bounds__(128, 8)
+k_step_tpe(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int32_t *__restrict__ actions,
+       const uint8_t *__restrict__ tape, float *__restrict__ obs, int32_t *__restrict__ reward,
+       uint8_t *__restrict__ done, int32_t *__restrict__ lines, int32_t *status, int flags, F8 dirs)
+{
+    __shared__ uint32_t s_ori[32], s_piece[16];
+    __shared__ __align__(16) uint32_t s_run[RunTab<R>::SIZE];
+    for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) s_run[m] = g_run<R>.v[m];
+    stage_tables(s_ori, s_piece);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= sv.n_env) return;
+    uint32_t col[C];
+    load_board<C, R>(sv, e, col);
+    Meta mt = unpack_meta(sv.meta[e]);
+    uint2 ep = sv.epi[e];
+    const bool live = mt.piece < kNumPieces;                                  // not a finished rollout fork
+    const uint32_t pw = s_piece[live ? mt.piece : 0];
+    const int action = actions[e];
+    const unsigned long long vm = live ? valid_mask<C, R>(col, pw, s_ori) : 0ull;   // game.py:69
+    int sel = -1;
+    if (action >= 0) {
+        if (flags & TB_FLAG_ACTION_IS_SLOT) {
+            if (action < 64 && ((vm >> action) & 1ull)) sel = action;
+        } else if (action < __popcll(vm)) {
+            sel = nth_set_bit(vm, action);                                    // game.py:83
+        }
+    }
+    if (sel < 0) {
+        // IndexError in the reference (game.py:83).  The env is left untouched, its outputs are defined (zero
+        // observation / reward / lines; done = it has no legal placement at all), and status reports the lowest
+        // offending env as 0x7FFFFFFF - env.
+        if (status) atomicMax(status, 0x7FFFFFFF - (int)(e < 0x7FFFFFFE ? e : 0x7FFFFFFE));
+        if (!(flags & TB_FLAG_VALIDATE_ONLY)) {
+            if (obs) {
+                float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
+                o[0] = make_float4(0.f, 0.f, 0.f, 0.f); o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (reward) reward[e] = 0;
+            if (done) done[e] = (uint8_t)(vm == 0ull);
+            if (lines) lines[e] = 0;
+        }
+        return;
+    }
+    if (flags & TB_FLAG_VALIDATE_ONLY) return;                                // dry run: only the status is produced
+    int ori, c;
+    slot_to_placement(pw, C, sel, ori, c);
+    Eval ev;
+    eval_slow<C, R>(col, s_ori[ori], c, ev, col, s_run);                             // current_state = afterstates[action]
+    const int lc = popc32(ev.full);                                           // game.py:85
+    int rew = lc - 1;                                                         // game.py:86
+    const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
+    mt.piece = draw_piece(piece_set, key, mt, tape, e);                       // game.py:87
+    const bool dn = mt.piece >= kNumPieces || !any_valid<C, R>(col, s_piece[mt.piece], s_ori);   // game.py:88,94-100
+    if (dn) rew -= 100;                                                       // game.py:89-90
+    ep.x += 1u; ep.y += (uint32_t)lc;
+    if (obs) {
+        float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
+        o[0] = make_float4(ev.f[0] * dirs.v[0], ev.f[1] * dirs.v[1], ev.f[2] * dirs.v[2], ev.f[3] * dirs.v[3]);
+        o[1] = make_float4(ev.f[4] * dirs.v[4], ev.f[5] * dirs.v[5], ev.f[6] * dirs.v[6], ev.f[7] * dirs.v[7]);
+    }
+    if (reward) reward[e] = rew;
+    if (done) done[e] = (uint8_t)dn;
+    if (lines) lines[e] = lc;
+    if (dn && (flags & TB_FLAG_AUTO_RESET) && !tape) {                        // example_play.py:20-21
+#pragma unroll
+        for (int k = 0; k < C; ++k) col[k] = 0u;
+        mt.piece = draw_piece(piece_set, key, mt, nullptr, e);
         ep = make_uint2(0u, 0u);
     }
     store_board<C, R>(sv, e, col);
@@ -927,9 +1007,13 @@ apply_placement(uint32_t *col, Meta &mt, uint2 &ep, uint32_t d, int c, int piece
     return vm;
 }
 
-// (Round 2 tried the K2 scheme here -- a CTA steps a tile of envs in lockstep and pools the legality test of its tall envs
-// over the CTA, two barriers per step: 3.31 ms against 2.56 ms per 32 steps of 2^20 envs.  Independent threads with many
-// CTAs per SM hide the divergence better than lockstep removes it; profiles/README.md, r2d.)
+// (Round 2 tried two CTA-cooperative schemes here, both bit-exact and both slower than this kernel's 2.56 ms per 32 steps of
+// 2^20 envs: the K2 scheme -- a CTA steps a tile in lockstep and pools the legality test of its tall envs, two barriers
+// per step: 3.31 ms -- and re-packing the tile's envs over the lanes by height class every few steps so that warps are
+// all-low or all-tall: 3.45 ms re-packing every 4 steps, 2.76 ms never re-packing (256-thread CTAs).  40 % of the
+// warp-instructions here run with 5 of 32 lanes (the tall-board legality test), but warps progress at very different
+// rates and every CTA-level barrier makes all of them wait for the slowest: independent warps with 6 CTAs per SM hide the
+// divergence better than cooperation removes it.  profiles/README.md, r2d / r2k.)
 // random policy: everything is per-env, one thread per env, board in registers for all n_steps
 template <int C, int R>
 __global__ void __launch_bounds__(128, 6)                  // 80 registers, no spills (measured: profiles/README.md, r1g)
@@ -1470,6 +1554,15 @@ struct ShapeOps {
                 view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
         else if (cx->k2_cfg == 2)
             k_step<C, R, 256, 3><<<(unsigned)((n_env + 255) / 256), 256, 0, st>>>(
+                view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
+        else if (cx->k2_cfg == 5)
+            k_step_tpe<C, R><<<(unsigned)((n_env + 127) / 128), 128, 0, st>>>(
+                view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
+        else if (cx->k2_cfg == 3)
+            k_step<C, R, 64, 16><<<(unsigned)((n_env + 63) / 64), 64, 0, st>>>(
+                view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
+        else if (cx->k2_cfg == 4)
+            k_step<C, R, 32, 24><<<(unsigned)((n_env + 31) / 32), 32, 0, st>>>(
                 view(state, n_env), env_offset, seed, piece_set, actions, tape, obs, reward, done, lines, status, flags, one);
         else
             k_step<C, R, 256, 4><<<(unsigned)((n_env + 255) / 256), 256, 0, st>>>(
