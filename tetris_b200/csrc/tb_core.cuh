@@ -513,19 +513,41 @@ TB_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
     return c;
 #endif
 }
-// acc + run_sum(w), w < 2^R
+// acc + run_sum(w), w < 2^R.
+// On the device the table is ALWAYS in shared memory (every kernel stages it) and ALIGNED TO ITS SIZE, so that the
+// address of an entry is base | byte offset -- one LOP3 together with the mask of the chunk -- and the load is spelled
+// ld.shared on a 32-bit shared-space address.  (With a plain pointer ptxas sometimes keeps the table's base in a vector
+// register and adds it per lookup: +1 instruction on each of the ~9 lookups per afterstate.)
 template <int R>
 TB_HD uint32_t run_sum_acc(const uint32_t *tab, uint32_t w, uint32_t acc)
 {
     constexpr int HB = RunTab<R>::HB, NCH = RunTab<R>::NCH;
     constexpr uint32_t M = (uint32_t)(RunTab<R>::SIZE - 1);
     TB_CHECK((NCH * HB >= 32) || (w >> (NCH * HB)) == 0u);         // a well mask of a non-terminal board: below row R
-    if (NCH == 1) return acc + (tab[w] & 255u);
-    const uint32_t e0 = tab[w & M], e1 = tab[(w >> HB) & M];
+#if defined(__CUDA_ARCH__)
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tab);
+    TB_CHECK((base & (4u * M + 3u)) == 0u);
+    auto entry = [&](uint32_t byte_off) {                          // byte_off = 4 * index, already masked
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base | byte_off));
+        return v;
+    };
+    const uint32_t e0 = entry((w << 2) & (4u * M));
+    if (NCH == 1) return acc + (e0 & 255u);
+    const uint32_t e1 = entry(HB >= 2 ? (w >> (HB - 2)) & (4u * M) : ((w >> HB) & M) << 2);
+#else
+    const uint32_t e0 = tab[w & M];
+    if (NCH == 1) return acc + (e0 & 255u);
+    const uint32_t e1 = tab[(w >> HB) & M];
+#endif
     // e1 permuted to bytes [1, trail1, 0, rs1] against e0 = [rs0, lead0, trail0, 1]
     acc = dp4a_u(e0, prmt(e1, 0u, 0x0423), acc);
     if (NCH == 3) {
+#if defined(__CUDA_ARCH__)
+        const uint32_t e2 = entry((w >> (2 * HB - 2)) & (4u * M));
+#else
         const uint32_t e2 = tab[w >> (2 * HB)];
+#endif
         const uint32_t lead0 = (e0 >> 8) & 255u, lead1 = (e1 >> 8) & 255u, trail1 = (e1 >> 16) & 255u;
         const uint32_t carry = trail1 == (uint32_t)HB ? lead0 + (uint32_t)HB : lead1;   // run reaching chunk 2 from below
         acc += (e2 & 255u) + carry * ((e2 >> 16) & 255u);
@@ -713,7 +735,7 @@ TB_HD void load_neigh(const uint32_t *rec, int c, Neigh<C, R, W> &nb)
 struct OriU {
     int bot[4], len[4], top[4];   // per piece column: lowest cell offset, cell count, bot + len
     uint32_t seg[4];              // mask_lo(len) << bot: the column's cells relative to the anchor row
-    uint32_t mbot[4], mtop[4];    // mask_lo(bot), mask_lo(top)
+    uint32_t p2bot[4], p2top[4];  // 1 << bot, 1 << top: mask_lo(a + bot) = (1 << a) * p2bot - 1 is one multiply-add
     uint32_t chgm;                // mask_lo(len(changed_lines))
     int ph;                       // piece height
     uint32_t lh2;                 // 2 + 2 * landing_height_bonus + kFloatBias
@@ -722,7 +744,7 @@ struct OriU {
     // that many piece cells.  One value only: qb1 = qa1, mb = 0.
     uint32_t qa1, ma, qb1, mb;
 };
-constexpr int kOriWords = 32;     // OriU as flat words: bot[4] len[4] top[4] seg[4] mbot[4] mtop[4] chgm ph lh2 qa1 ma qb1 mb pad
+constexpr int kOriWords = 32;     // OriU as flat words: bot[4] len[4] top[4] seg[4] p2bot[4] p2top[4] chgm ph lh2 qa1 ma qb1 mb pad
 TB_HD OriU decode_ori(uint32_t d)
 {
     OriU u;
@@ -732,8 +754,8 @@ TB_HD OriU decode_ori(uint32_t d)
         u.len[dx] = desc_len(d, dx);
         u.top[dx] = u.bot[dx] + u.len[dx];
         u.seg[dx] = mask_lo(u.len[dx]) << u.bot[dx];
-        u.mbot[dx] = mask_lo(u.bot[dx]);
-        u.mtop[dx] = mask_lo(u.top[dx]);
+        u.p2bot[dx] = 1u << u.bot[dx];
+        u.p2top[dx] = 1u << u.top[dx];
     }
     u.chgm = mask_lo(desc_chg(d));
     u.ph = desc_ph(d);
@@ -768,7 +790,7 @@ constexpr OdescImage make_odesc_image()
         for (int dx = 0; dx < 4; ++dx) {
             const uint32_t bot = (d >> (3 + 5 * dx)) & 3u, len = (d >> (5 + 5 * dx)) & 7u, top = bot + len;
             t.w[i][0 + dx] = bot; t.w[i][4 + dx] = len; t.w[i][8 + dx] = top;
-            t.w[i][12 + dx] = cx_mask((int)len) << bot; t.w[i][16 + dx] = cx_mask((int)bot); t.w[i][20 + dx] = cx_mask((int)top);
+            t.w[i][12 + dx] = cx_mask((int)len) << bot; t.w[i][16 + dx] = 1u << bot; t.w[i][20 + dx] = 1u << top;
         }
         t.w[i][24] = cx_mask((int)((d >> 23) & 7u));                 // chgm
         t.w[i][25] = (d >> 28) & 7u;                                 // ph
@@ -805,6 +827,18 @@ constexpr RunImage<R> make_run_image()
     return t;
 }
 
+// 1 << a, opaque to the optimiser (which would turn x * (1 << a) back into a shift)
+TB_HD uint32_t pow2_opaque(int a)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t p;
+    asm("shl.b32 %0, 1, %1;" : "=r"(p) : "r"(a));
+    return p;
+#else
+    return 1u << a;
+#endif
+}
+
 // Incremental evaluation of one placement: orientation `u` (width W) anchored at column c.  Only the piece's
 // columns and their neighbours are re-evaluated; everything else comes from the env record.  Branch-free apart
 // from the two early exits.
@@ -822,8 +856,12 @@ TB_HD int eval_neigh(const uint32_t *rec, const uint32_t *runtab, const Neigh<C,
 #pragma unroll
     for (int dx = 0; dx < W; ++dx) a = imax(a, h[1 + dx] - u.bot[dx]);          // tetromino.py: anchor_row = max(h - bottom)
 
+    // Shifts by the anchor row as multiplications by 2^a: the kernels are bound by the half-rate ALU pipe (LOP3 / SHF /
+    // IADD3: 67 % busy in K1) while the multiply-add pipe idles at 18 %, so `x << a` = x * p2a and the masks
+    // mask_lo(a + k) = p2a * 2^k - 1 each become ONE IMAD on the other pipe (profiles/README.md, r2m).
+    const uint32_t p2a = pow2_opaque(a);
     // rows among changed_lines that the placement completes: empty cells before == piece cells added (see build_env)
-    const uint32_t full = (rec[K::FQ + u.qa1] & (u.ma << a)) | (rec[K::FQ + u.qb1] & (u.mb << a));
+    const uint32_t full = (rec[K::FQ + u.qa1] & (u.ma * p2a)) | (rec[K::FQ + u.qb1] & (u.mb * p2a));
     const int top = a + u.ph;
     e.a = a; e.full = full;
     if (full != 0u) {
@@ -835,7 +873,6 @@ TB_HD int eval_neigh(const uint32_t *rec, const uint32_t *runtab, const Neigh<C,
     if (top > R) { e.terminal = 1; return kFastTerminal; }
     e.terminal = 0;
 
-    const uint32_t ma = mask_lo(a);
     int gapsum = 0, gapcnt = 0, hdadd = 0;
     uint32_t gapor = 0;
     uint32_t mt[W];                                                // mask_lo(new height) of the piece columns
@@ -843,13 +880,14 @@ TB_HD int eval_neigh(const uint32_t *rec, const uint32_t *runtab, const Neigh<C,
     for (int dx = 0; dx < W; ++dx) {
         const int len = u.len[dx], lo = a + u.bot[dx], hh = h[1 + dx];
         const int g = lo - hh;                                     // new holes under the piece in this column
-        y[2 + dx] |= u.seg[dx] << a;
+        const int g1 = imin(g, 1);                                 // g > 0 (g is never negative: a = max(h - bot))
+        y[2 + dx] += u.seg[dx] * p2a;                              // the cells land on empty cells: OR = ADD
         gapsum += g;
-        gapcnt += (g > 0);
-        gapor |= ((ma << u.bot[dx]) | u.mbot[dx]) ^ nb.mh[dx];     // rows hh .. lo-1
-        hdadd += len * (nb.nr[dx] + (g > 0));
+        gapcnt += g1;
+        gapor |= (p2a * u.p2bot[dx] - 1u) ^ nb.mh[dx];             // rows hh .. lo-1
+        hdadd += len * (nb.nr[dx] + g1);
         h[1 + dx] = lo + len;
-        mt[dx] = (ma << u.top[dx]) | u.mtop[dx];
+        mt[dx] = p2a * u.p2top[dx] - 1u;
     }
 
     // wells over columns c-1 .. c+W, row transitions over columns c .. c+W; the sentinels make the walls come out right

@@ -248,6 +248,17 @@ template <int TILE, int THREADS = TILE> struct BestSmem {
 static __device__ const OdescImage g_odesc = make_odesc_image();
 template <int R> static __device__ const RunImage<R> g_run = make_run_image<R>();
 
+// The run-sum table must sit at a shared-memory ADDRESS that is a multiple of its size (run_sum_acc forms entry addresses
+// with OR).  The shared window of a CTA does not start at a multiple of 4 KB (the first 1 KB is the system's), so the
+// alignment of a static array says nothing about its address: the table gets twice its size and is placed at run time.
+template <int R>
+__device__ __forceinline__ uint32_t *run_tab_place(uint32_t *raw)
+{
+    constexpr uint32_t BYTES = (uint32_t)RunTab<R>::SIZE * 4u;
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(raw);
+    return raw + (((0u - a) & (BYTES - 1u)) >> 2);
+}
+
 // s_run: the run-sum table, in STATIC shared memory (its address is then an immediate of every lookup; inside the
 // dynamic block each of the ~9 lookups per afterstate paid an add of the block's base)
 template <int C, int R, int TILE>
@@ -417,7 +428,8 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     static_assert(TILE % 32 == 0 && THREADS % TILE == 0, "TILE: whole warps of envs; THREADS: a multiple of TILE");
     constexpr int NWARPS = THREADS / 32, NGROUPS = TILE / 32;
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
-    __shared__ __align__(16) uint32_t s_run[RunTab<R>::SIZE];
+    __shared__ __align__(16) uint32_t s_run_raw[2 * RunTab<R>::SIZE];
+    uint32_t *const s_run = run_tab_place<R>(s_run_raw);
     stage_cta(sm, s_run);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool env_thread = THREADS == TILE || tid < TILE;   // this thread owns env `tid` of the tile in the per-env phases
@@ -663,7 +675,7 @@ k_afterstates_export(StateView sv, float *__restrict__ feats, uint16_t *__restri
 template <int C, int R, int TILE>
 struct StepSmem {
     uint32_t cols[TILE][C | 1];          // columns of the listed envs (odd stride)
-    alignas(16) uint32_t run[RunTab<R>::SIZE];
+    alignas(16) uint32_t run_raw[2 * RunTab<R>::SIZE];   // the table is placed inside at a multiple of its size
     unsigned long long vmask[TILE];      // by env: legal slots, written by the pooled phase
     uint16_t list[TILE];                 // listed (tall) envs of the current pass
     uint8_t lpiece[TILE];                // by env: piece to test in the pooled phase
@@ -683,7 +695,8 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
     if (tid < kNumOris) sm.ori[tid] = c_ori[tid];
     if (tid < kNumPieces) sm.piece[tid] = c_piece[tid];
     if (tid < 2) sm.n_list[tid] = 0;
-    for (int m = tid; m < RunTab<R>::SIZE; m += TILE) sm.run[m] = g_run<R>.v[m];
+    uint32_t *const s_run = run_tab_place<R>(sm.run_raw);
+    for (int m = tid; m < RunTab<R>::SIZE; m += TILE) s_run[m] = g_run<R>.v[m];
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * TILE + tid;
     const bool in_range = e < sv.n_env;
@@ -741,7 +754,7 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
                 int ori, c;
                 slot_to_placement(pw, C, sel, ori, c);
                 Eval ev;
-                eval_slow<C, R>(col, sm.ori[ori], c, ev, col, sm.run);       // current_state = afterstates[action]
+                eval_slow<C, R>(col, sm.ori[ori], c, ev, col, s_run);       // current_state = afterstates[action]
                 lc = popc32(ev.full);                                         // game.py:85
                 if (obs) {                                                    // game.py:91 (stored here: fewer live registers)
                     float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
@@ -804,7 +817,8 @@ k_step_tpe(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const
        uint8_t *__restrict__ done, int32_t *__restrict__ lines, int32_t *status, int flags, F8 dirs)
 {
     __shared__ uint32_t s_ori[32], s_piece[16];
-    __shared__ __align__(16) uint32_t s_run[RunTab<R>::SIZE];
+    __shared__ __align__(16) uint32_t s_run_raw[2 * RunTab<R>::SIZE];
+    uint32_t *const s_run = run_tab_place<R>(s_run_raw);
     for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) s_run[m] = g_run<R>.v[m];
     stage_tables(s_ori, s_piece);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1090,7 +1104,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
     BestSmem<TILE, THREADS> &bs =
         *reinterpret_cast<BestSmem<TILE, THREADS> *>(smem_raw + ((sizeof(CtaSmem<C, R, TILE>) + 15) & ~(size_t)15));
-    __shared__ __align__(16) uint32_t s_run[RunTab<R>::SIZE];
+    __shared__ __align__(16) uint32_t s_run_raw[2 * RunTab<R>::SIZE];
+    uint32_t *const s_run = run_tab_place<R>(s_run_raw);
     stage_cta(sm, s_run);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool env_thread = THREADS == TILE || tid < TILE;   // this thread owns env `tid` of the tile in the per-env phases
