@@ -17,9 +17,15 @@ static int afterstates_t(int piece, const uint16_t *rows, int mode, float *feats
     for (int r = 0; r < S::N; ++r) w[r >> 1] |= (uint32_t)rows[r] << (16 * (r & 1));
     uint32_t col[C];
     rows_to_cols<C, R>(w, col);
-    static uint32_t runtab[RunTab<R>::SIZE];
+    static uint32_t runtab[RunTab<R>::WORDS];
     static bool init = false;
-    if (!init) { for (int m = 0; m < RunTab<R>::SIZE; ++m) runtab[m] = run_tab_entry<R>((uint32_t)m); init = true; }
+    if (!init) {
+        for (int m = 0; m < RunTab<R>::SIZE; ++m) {
+            runtab[m] = run_tab_entry<R>((uint32_t)m);
+            if (RunTab<R>::COPIES == 2) runtab[RunTab<R>::SIZE + m] = prmt(runtab[m], 0u, 0x0423);   // the permuted copy
+        }
+        init = true;
+    }
     uint32_t rec[Env<C, R>::WORDS + 8];
     std::memset(rec, 0, sizeof rec);
     uint32_t any = 0;
@@ -115,8 +121,10 @@ template <int R>
 static int run_image_ok()
 {
     static constexpr RunImage<R> img = make_run_image<R>();
-    for (int m = 0; m < RunTab<R>::SIZE; ++m)
+    for (int m = 0; m < RunTab<R>::SIZE; ++m) {
         if (img.v[m] != run_tab_entry<R>((uint32_t)m)) return 0;
+        if (RunTab<R>::COPIES == 2 && img.v[RunTab<R>::SIZE + m] != prmt(run_tab_entry<R>((uint32_t)m), 0u, 0x0423)) return 0;
+    }
     return 1;
 }
 extern "C" int hc_table_images()

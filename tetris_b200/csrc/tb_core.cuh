@@ -451,11 +451,12 @@ TB_HD int place_and_clear(uint32_t *col, uint32_t d, int c, int &a_out, uint32_t
 
 // Slow (general) path: build the afterstate board, clear, evaluate from scratch.
 // `col` is the current board (not modified unless out_col == col); out_col (nullable) gets the afterstate.
-template <int C, int R>
+template <int C, int R, bool PERM = true>
 TB_HD void eval_full_tab(const uint32_t *col, const uint32_t *runtab, int *out6);   // below, after the run-sum table
 
 // runtab (nullable): the run-sum table; with it the afterstate must be NON-TERMINAL (eval_full_tab).
-template <int C, int R>
+// PERM: the table carries its byte-permuted second copy (RunTab::COPIES; K2 stages the plain table only).
+template <int C, int R, bool PERM = true>
 TB_HD void eval_slow(const uint32_t *col, uint32_t d, int c, Eval &e, uint32_t *out_col, const uint32_t *runtab = nullptr)
 {
     uint32_t nc[C];
@@ -463,7 +464,7 @@ TB_HD void eval_slow(const uint32_t *col, uint32_t d, int c, Eval &e, uint32_t *
     for (int k = 0; k < C; ++k) nc[k] = col[k];
     const int cells = place_and_clear<C, R>(nc, d, c, e.a, e.full, e.terminal);
     int six[6];
-    if (runtab) eval_full_tab<C, R>(nc, runtab, six);
+    if (runtab) eval_full_tab<C, R, PERM>(nc, runtab, six);
     else eval_full<C, R>(nc, six);
     const int ncl = popc32(e.full);
     e.f[0] = (float)six[0]; e.f[1] = (float)six[1]; e.f[2] = (float)six[2];
@@ -492,6 +493,10 @@ struct RunTab {
     static constexpr int NCH = R <= 10 ? 1 : (R <= 20 ? 2 : 3);
     static constexpr int HB = (R + NCH - 1) / NCH;
     static constexpr int SIZE = 1 << HB;
+    // two-chunk boards keep a second copy with every entry already byte-permuted into the form the dot product wants
+    // of the HIGH chunk ([1, trail, 0, run_sum]): one PRMT less per lookup pair
+    static constexpr int COPIES = NCH == 2 ? 2 : 1;
+    static constexpr int WORDS = COPIES * SIZE;
     static_assert(HB <= 10 && R <= 27, "run table: chunks of at most 10 rows, boards of at most 27 rows");
 };
 template <int R>
@@ -518,7 +523,7 @@ TB_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
 // address of an entry is base | byte offset -- one LOP3 together with the mask of the chunk -- and the load is spelled
 // ld.shared on a 32-bit shared-space address.  (With a plain pointer ptxas sometimes keeps the table's base in a vector
 // register and adds it per lookup: +1 instruction on each of the ~9 lookups per afterstate.)
-template <int R>
+template <int R, bool PERM = true>
 TB_HD uint32_t run_sum_acc(const uint32_t *tab, uint32_t w, uint32_t acc)
 {
     constexpr int HB = RunTab<R>::HB, NCH = RunTab<R>::NCH;
@@ -534,10 +539,17 @@ TB_HD uint32_t run_sum_acc(const uint32_t *tab, uint32_t w, uint32_t acc)
     };
     const uint32_t e0 = entry((w << 2) & (4u * M));
     if (NCH == 1) return acc + (e0 & 255u);
-    const uint32_t e1 = entry(HB >= 2 ? (w >> (HB - 2)) & (4u * M) : ((w >> HB) & M) << 2);
+    const uint32_t off1 = HB >= 2 ? (w >> (HB - 2)) & (4u * M) : ((w >> HB) & M) << 2;
+    if (NCH == 2 && PERM) {                                        // the permuted copy sits SIZE entries further
+        uint32_t e1p;
+        asm("ld.shared.u32 %0, [%1+%2];" : "=r"(e1p) : "r"(base | off1), "n"(4 * RunTab<R>::SIZE));
+        return dp4a_u(e0, e1p, acc);
+    }
+    const uint32_t e1 = entry(off1);
 #else
     const uint32_t e0 = tab[w & M];
     if (NCH == 1) return acc + (e0 & 255u);
+    if (NCH == 2 && PERM) return dp4a_u(e0, tab[RunTab<R>::SIZE + ((w >> HB) & M)], acc);
     const uint32_t e1 = tab[(w >> HB) & M];
 #endif
     // e1 permuted to bytes [1, trail1, 0, rs1] against e0 = [rs0, lead0, trail0, 1]
@@ -559,7 +571,7 @@ TB_HD int run_sum_tab(const uint32_t *tab, uint32_t w) { return (int)run_sum_acc
 
 // eval_full for NON-TERMINAL boards (every column height <= R: well masks stay below row R), cumulative wells by table:
 // no data-dependent POPC loop, so the lanes of a warp stay together.  Same out6 as eval_full.
-template <int C, int R>
+template <int C, int R, bool PERM>
 TB_HD void eval_full_tab(const uint32_t *col, const uint32_t *runtab, int *out6)
 {
     using S = Shape<C, R>;
@@ -582,7 +594,7 @@ TB_HD void eval_full_tab(const uint32_t *col, const uint32_t *runtab, int *out6)
             hd += popc32(x >> (r + 1));
             t &= t - 1;
         }
-        wells = run_sum_acc<R>(runtab, L & Rt & ~x, wells);      // :222-233,:262-272 (heights <= R: no limit mask needed)
+        wells = run_sum_acc<R, PERM>(runtab, L & Rt & ~x, wells);   // :222-233,:262-272 (heights <= R: no limit mask needed)
         if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh); // :203-204,:225-226,:246-248
         else rt += popc32(L & mask_lo(hL));                      // :254
         L = x; hL = h;
@@ -809,7 +821,11 @@ constexpr OdescImage make_odesc_image()
     return t;
 }
 
-template <int R> struct RunImage { alignas(16) uint32_t v[RunTab<R>::SIZE]; };
+template <int R> struct RunImage { alignas(16) uint32_t v[RunTab<R>::WORDS]; };
+constexpr uint32_t run_tab_permuted(uint32_t e)                    // prmt(e, 0, 0x0423): bytes [e3, e2, 0, e0]
+{
+    return (e >> 24) | (((e >> 16) & 255u) << 8) | ((e & 255u) << 24);
+}
 template <int R>
 constexpr RunImage<R> make_run_image()
 {
@@ -823,6 +839,7 @@ constexpr RunImage<R> make_run_image()
         while (trail < HB && ((m >> trail) & 1)) ++trail;
         while (lead < HB && ((m >> (HB - 1 - lead)) & 1)) ++lead;
         t.v[m] = (uint32_t)rs | ((uint32_t)lead << 8) | ((uint32_t)trail << 16) | (1u << 24);
+        if (RunTab<R>::COPIES == 2) t.v[RunTab<R>::SIZE + m] = run_tab_permuted(t.v[m]);
     }
     return t;
 }

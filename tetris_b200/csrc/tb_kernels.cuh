@@ -259,6 +259,20 @@ __device__ __forceinline__ uint32_t *run_tab_place(uint32_t *raw)
     return raw + (((0u - a) & (BYTES - 1u)) >> 2);
 }
 
+// copy the table image (128-bit words where the size allows); the caller synchronises
+template <int R, bool PERM = true>
+__device__ __forceinline__ void stage_run_table(uint32_t *s_run)
+{
+    constexpr int N = PERM ? RunTab<R>::WORDS : RunTab<R>::SIZE;   // with or without the permuted second copy
+    if (N % 4 == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_run<R>.v);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_run);
+        for (int i = threadIdx.x; i < N / 4; i += blockDim.x) dst[i] = src[i];
+    } else {
+        for (int m = threadIdx.x; m < N; m += blockDim.x) s_run[m] = g_run<R>.v[m];
+    }
+}
+
 // s_run: the run-sum table, in STATIC shared memory (its address is then an immediate of every lookup; inside the
 // dynamic block each of the ~9 lookups per afterstate paid an add of the block's base)
 template <int C, int R, int TILE>
@@ -282,13 +296,7 @@ __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm, uint32_t *s_r
         sm.job[threadIdx.x] = jb;
     }
     if (threadIdx.x <= kNumPieces) { sm.cnt[0][threadIdx.x] = 0; sm.cnt[1][threadIdx.x] = 0; }
-    if (RunTab<R>::SIZE % 4 == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(g_run<R>.v);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_run);
-        for (int i = threadIdx.x; i < RunTab<R>::SIZE / 4; i += blockDim.x) dst[i] = src[i];
-    } else {
-        for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) s_run[m] = g_run<R>.v[m];
-    }
+    stage_run_table<R>(s_run);
     __syncthreads();
 }
 
@@ -428,7 +436,7 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
     static_assert(TILE % 32 == 0 && THREADS % TILE == 0, "TILE: whole warps of envs; THREADS: a multiple of TILE");
     constexpr int NWARPS = THREADS / 32, NGROUPS = TILE / 32;
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
-    __shared__ __align__(16) uint32_t s_run_raw[2 * RunTab<R>::SIZE];
+    __shared__ __align__(16) uint32_t s_run_raw[RunTab<R>::SIZE + RunTab<R>::WORDS];
     uint32_t *const s_run = run_tab_place<R>(s_run_raw);
     stage_cta(sm, s_run);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -675,7 +683,8 @@ k_afterstates_export(StateView sv, float *__restrict__ feats, uint16_t *__restri
 template <int C, int R, int TILE>
 struct StepSmem {
     uint32_t cols[TILE][C | 1];          // columns of the listed envs (odd stride)
-    alignas(16) uint32_t run_raw[2 * RunTab<R>::SIZE];   // the table is placed inside at a multiple of its size
+    alignas(16) uint32_t run_raw[2 * RunTab<R>::SIZE];   // the plain table (no permuted copy: a CTA here handles one tile
+                                                         // and staging 8 KB more costs 5 %), placed at a multiple of its size
     unsigned long long vmask[TILE];      // by env: legal slots, written by the pooled phase
     uint16_t list[TILE];                 // listed (tall) envs of the current pass
     uint8_t lpiece[TILE];                // by env: piece to test in the pooled phase
@@ -696,7 +705,7 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
     if (tid < kNumPieces) sm.piece[tid] = c_piece[tid];
     if (tid < 2) sm.n_list[tid] = 0;
     uint32_t *const s_run = run_tab_place<R>(sm.run_raw);
-    for (int m = tid; m < RunTab<R>::SIZE; m += TILE) s_run[m] = g_run<R>.v[m];
+    stage_run_table<R, false>(s_run);
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * TILE + tid;
     const bool in_range = e < sv.n_env;
@@ -754,7 +763,7 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
                 int ori, c;
                 slot_to_placement(pw, C, sel, ori, c);
                 Eval ev;
-                eval_slow<C, R>(col, sm.ori[ori], c, ev, col, s_run);       // current_state = afterstates[action]
+                eval_slow<C, R, false>(col, sm.ori[ori], c, ev, col, s_run);       // current_state = afterstates[action]
                 lc = popc32(ev.full);                                         // game.py:85
                 if (obs) {                                                    // game.py:91 (stored here: fewer live registers)
                     float4 *o = reinterpret_cast<float4 *>(obs + e * 8);
@@ -774,7 +783,10 @@ k_step(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const int
             TB_CHECK(li >= 0 && li < TILE);
             sm.list[li] = (uint16_t)tid;
         }
+        // the barrier that completes the list also tells whether the tile listed anything: on low boards (greedy play)
+        // most tiles list nothing and skip the pooled phase together with its second barrier
         __syncthreads();
+        if (sm.n_list[pass] == 0) continue;
         // ---- pooled: legal slots of the listed envs (game.py:69 / :94-100), one thread per list entry.  (Measured and
         // rejected, profiles/README.md r2f / r2l: a warp per entry with lane = enumeration slot -- shorter wait at the
         // barrier, more instructions in total, 0.148 vs 0.122 ms; split barriers where only the consumer warps and the
@@ -819,7 +831,7 @@ k_step_tpe(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const
     __shared__ uint32_t s_ori[32], s_piece[16];
     __shared__ __align__(16) uint32_t s_run_raw[2 * RunTab<R>::SIZE];
     uint32_t *const s_run = run_tab_place<R>(s_run_raw);
-    for (int m = threadIdx.x; m < RunTab<R>::SIZE; m += blockDim.x) s_run[m] = g_run<R>.v[m];
+    stage_run_table<R, false>(s_run);
     stage_tables(s_ori, s_piece);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= sv.n_env) return;
@@ -859,7 +871,7 @@ k_step_tpe(StateView sv, int64_t env_offset, uint64_t seed, int piece_set, const
     int ori, c;
     slot_to_placement(pw, C, sel, ori, c);
     Eval ev;
-    eval_slow<C, R>(col, s_ori[ori], c, ev, col, s_run);                             // current_state = afterstates[action]
+    eval_slow<C, R, false>(col, s_ori[ori], c, ev, col, s_run);                             // current_state = afterstates[action]
     const int lc = popc32(ev.full);                                           // game.py:85
     int rew = lc - 1;                                                         // game.py:86
     const uint64_t key = env_key(seed, (uint64_t)(env_offset + e));
@@ -1104,7 +1116,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
     CtaSmem<C, R, TILE> &sm = *reinterpret_cast<CtaSmem<C, R, TILE> *>(smem_raw);
     BestSmem<TILE, THREADS> &bs =
         *reinterpret_cast<BestSmem<TILE, THREADS> *>(smem_raw + ((sizeof(CtaSmem<C, R, TILE>) + 15) & ~(size_t)15));
-    __shared__ __align__(16) uint32_t s_run_raw[2 * RunTab<R>::SIZE];
+    __shared__ __align__(16) uint32_t s_run_raw[RunTab<R>::SIZE + RunTab<R>::WORDS];
     uint32_t *const s_run = run_tab_place<R>(s_run_raw);
     stage_cta(sm, s_run);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
