@@ -13,6 +13,7 @@ for k in "$@"; do
   case $k in
     k1) cap k1 k_afterstates 1 k_afterstatesILi10ELi20ELi0ELi256ELi3ELi256E ;;
     k3) cap k3 k_rollout_greedy 2 k_rollout_greedyILi10ELi20ELi256ELi3ELi256E ;;
+    k3g) cap k3g k_rollout_greedy 5 k_rollout_greedyILi10ELi20ELi256ELi3ELi256E ;;   # 8 steps in the greedy steady state
     k2) cap k2 k_step 1 k_stepILi10ELi20ELi256ELi4E ;;
     k3r) cap k3r k_rollout_random 1 k_rollout_randomILi10ELi20EE ;;
   esac

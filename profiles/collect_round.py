@@ -19,6 +19,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us":
 WORKLOAD = {
     "k1": "profiles/prof_run.py: tb_afterstates over 2^20 envs, 10x20, 7-piece, boards after greedy play (bench.py's roofline leg)",
     "k3": "profiles/prof_run.py: tb_rollout greedy, 8 placements per env over 2^20 envs, 10x20, 7-piece, boards after random play",
+    "k3g": "profiles/prof_run.py: tb_rollout greedy, 8 placements per env over 2^20 envs, 10x20, 7-piece, boards in the greedy steady state (what bench.py's timed region sees)",
     "k2": "profiles/prof_run.py: tb_step (action 0) over 2^20 envs, 10x20, 7-piece, boards after greedy play",
     "k3r": "profiles/prof_run.py: tb_rollout random, 8 placements per env over 2^20 envs, 10x20, 7-piece",
 }
@@ -56,7 +57,7 @@ def parse_summary(path):
 def main():
     from tetris_b200 import _lib
     tag = sys.argv[1]
-    kernels = sys.argv[2:] or ["k1", "k3", "k2", "k3r"]
+    kernels = sys.argv[2:] or ["k1", "k3", "k3g", "k2", "k3r"]
     for k in kernels:
         for t in ("lines", "stalls", "summary"):
             src = os.path.join(OUT, "%s_%s_%s.txt" % (tag, k, t))

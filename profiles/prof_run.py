@@ -26,5 +26,9 @@ for _ in range(2):
     feats, valid, count = env.get_after_states()
 for _ in range(2):
     env.step(torch.zeros(n, dtype=torch.int32, device="cuda"), auto_reset=True, check=False)
+# steady-state greedy play (what bench.py's timed region sees): greedy launches 3 (warm-up to the steady state), 4 and 5
+env.rollout(600, "greedy")
+for _ in range(2):
+    env.rollout(T, "greedy")
 torch.cuda.synchronize()
 print("ok", env.stats_dict())

@@ -246,6 +246,26 @@ template <int TILE, int THREADS = TILE> struct BestSmem {
 // decode_ori / run_tab_entry on the CPU by tests/hostcheck), copied -- not computed -- by every CTA: with multi-wave
 // grids a CTA often handles a single tile, and building the run table in the kernel cost about 3 % of a K1 tile.
 static __device__ const OdescImage g_odesc = make_odesc_image();
+// The same image and the job table in CONSTANT memory, for K1's phase B: its descriptor fields and job words then come from
+// the constant cache (LDC) instead of shared memory, whose pipe K1 needs for the env records and the run table
+// (K1 -2.8 %; K3, measured the same way, +3.3 %: it keeps the shared-memory copies.  profiles/README.md, r2t).
+static __constant__ OdescImage c_odesc = make_odesc_image();
+struct JobImage { uint32_t v[kNumJobs]; };
+template <int C>
+constexpr JobImage make_job_image()
+{
+    JobImage t{};
+    for (int i = 0; i < kNumJobs; ++i) {
+        const int p = i >> 1, l = i & 1;
+        const uint32_t pw = kPieceHost[p];
+        const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, w1 = (pw >> 7) & 7, obase = (pw >> 10) & 63;
+        const int n = l ? n1 : n0, w = l ? w1 : w0, ob = l ? obase + n0 : obase, sbase = l ? n0 * (C - w0 + 1) : 0;
+        t.v[i] = (uint32_t)p | (uint32_t)l << 4 | (uint32_t)w << 5 | (uint32_t)(w <= C ? n : 0) << 8 |
+                 (uint32_t)ob << 10 | (uint32_t)sbase << 16;
+    }
+    return t;
+}
+template <int C> static __constant__ JobImage c_job = make_job_image<C>();
 template <int R> static __device__ const RunImage<R> g_run = make_run_image<R>();
 
 // The run-sum table must sit at a shared-memory ADDRESS that is a multiple of its size (run_sum_acc forms entry addresses
@@ -367,6 +387,14 @@ __device__ __forceinline__ void for_each_slow_item(uint32_t m0, uint32_t m1, int
     }
 }
 
+// vloc / sloc words hold, per orientation, the warp ballot shifted down to the env's first lane and cut to 16 bits by the
+// store: bits at and above the loop's column count belong to the next env of the window.  Readers mask with this.
+template <int C>
+__device__ __forceinline__ uint32_t loc_mask(uint32_t pw, int l)
+{
+    const int w = (int)((pw >> (l ? 7 : 2)) & 7u);
+    return ((1u << (C - w + 1)) - 1u) * 0x00010001u;
+}
 // legal columns per orientation (16 bits each, orientation-major) -> loop-local slot bits c * n + o
 __device__ __forceinline__ uint32_t slots_of(uint32_t v, int n)
 {
@@ -502,11 +530,14 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 TB_CHECK(env < sv.n_env && (int)sm.pid[slot] == (int)(jb & 15u));
                 Neigh<C, R, W> nb;
                 load_neigh<C, R, W>(rec, c, nb);
-                uint32_t vsel = 0u, ssel = 0u;              // leader lane: legal / slow columns of its env, 16 bits per orientation
+                // leader lane: legal / slow columns of its env, stored per orientation as the 16-bit halves of vloc / sloc
+                uint16_t *const v16 = reinterpret_cast<uint16_t *>(&sm.vloc[slot][l]);
+                uint16_t *const s16 = reinterpret_cast<uint16_t *>(&sm.sloc[slot][l]);
+                const bool leader = on && c == 0;
 #pragma unroll 1
                 for (int o = 0; o < n; ++o) {
                     const int oi = (int)((jb >> 10) & 63u) + o;
-                    const OriU &u = *reinterpret_cast<const OriU *>(sm.odesc[oi]);
+                    const OriU &u = *reinterpret_cast<const OriU *>(c_odesc.w[oi]);
                     const int aslot = (int)(jb >> 16) + c * n + o;
                     bool slow = false, legal = false;
                     if (on) {
@@ -517,17 +548,17 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                         else slow = want_terminal && aslot < a_stride;
                         legal = !ev.terminal;
                     }
-                    vsel |= ((__ballot_sync(FULLMASK, legal) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
-                    ssel |= ((__ballot_sync(FULLMASK, slow) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
+                    const uint32_t bl = __ballot_sync(FULLMASK, legal) >> (k * NC);      // cut to the env's columns by the readers
+                    const uint32_t bw = __ballot_sync(FULLMASK, slow) >> (k * NC);
+                    if (leader) { v16[o] = (uint16_t)bl; s16[o] = (uint16_t)bw; }
                 }
-                if (on && c == 0) { sm.vloc[slot][l] = vsel; sm.sloc[slot][l] = ssel; }
             }
         };
         {
             int pbase = 0;
 #pragma unroll 1
             for (int j = 0; j < kNumJobs; ++j) {
-                const uint32_t jb = sm.job[j];
+                const uint32_t jb = c_job<C>.v[j];
                 const int np = cnt[jb & 15];
                 if (np != 0 && ((jb >> 8) & 3u) != 0u) {
                     switch ((jb >> 5) & 7u) {
@@ -550,7 +581,11 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
 #pragma unroll
             for (int q = 0; q < kNumPieces; ++q) n_active += cnt[q];
             uint32_t m0 = 0u, m1 = 0u;
-            if (env_thread && tid < n_active) { m0 = sm.sloc[tid][0]; m1 = sm.sloc[tid][1]; }
+            if (env_thread && tid < n_active) {                // slot tid: cut the marks to the loops' columns, for all readers
+                const uint32_t pw = sm.piece[sm.pid[tid]];
+                m0 = sm.sloc[tid][0] & loc_mask<C>(pw, 0); m1 = sm.sloc[tid][1] & loc_mask<C>(pw, 1);
+                sm.sloc[tid][0] = m0; sm.sloc[tid][1] = m1;
+            }
             int incl = __popc(m0) + __popc(m1);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -604,8 +639,8 @@ afterstates_body(const StateView &sv, float *__restrict__ feats, unsigned long l
                 const uint32_t pw = sm.piece[piece];
                 const int n0 = (int)(pw & 3u), n1 = (int)((pw >> 5) & 3u);
                 const int s1 = n0 * (C - (int)((pw >> 2) & 7u) + 1);
-                v = (unsigned long long)slots_of(sm.vloc[myslot][0], n0) |
-                    ((unsigned long long)slots_of(sm.vloc[myslot][1], n1) << s1);
+                v = (unsigned long long)slots_of(sm.vloc[myslot][0] & loc_mask<C>(pw, 0), n0) |
+                    ((unsigned long long)slots_of(sm.vloc[myslot][1] & loc_mask<C>(pw, 1), n1) << s1);
             }
             if (valid_out) valid_out[e] = v;
             if (count_out) count_out[e] = __popcll(v);
@@ -1191,7 +1226,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     load_neigh<C, R, W>(rec, c, nb);
                     uint32_t best_ord = 0u;                // this lane's best orderable score (0 = none) and its slot
                     int best_slot = 0;
-                    uint32_t ssel = 0u;                    // leader lane: line-clearing legal placements of its env
+                    uint16_t *const s16 = reinterpret_cast<uint16_t *>(&sm.sloc[slot][l]);
+                    const bool leader = on && c == 0;
 #pragma unroll 1
                     for (int o = 0; o < n; ++o) {
                         const int oi = (int)((jb >> 10) & 63u) + o;
@@ -1208,7 +1244,8 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                                 slow = !ev.terminal;
                             }
                         }
-                        ssel |= ((__ballot_sync(FULLMASK, slow) >> (k * NC)) & ((1u << NC) - 1u)) << (16 * o);
+                        const uint32_t bw = __ballot_sync(FULLMASK, slow) >> (k * NC);   // cut to the env's columns by phase S
+                        if (leader) s16[o] = (uint16_t)bw;
                     }
                     // first arg-max over the env's NC lanes: highest score, then lowest slot (= lowest column, then o)
                     uint32_t m = best_ord;
@@ -1221,7 +1258,7 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
                     const uint32_t hit = (__ballot_sync(FULLMASK, best_ord == m) >> (k * NC)) & ((1u << NC) - 1u);
                     const int src = k * NC + __ffs((int)hit) - 1;              // lowest column that reaches it
                     const int sl = __shfl_sync(FULLMASK, best_slot, src & 31);
-                    if (on && c == 0) { sm.vloc[slot][l] = m; bs.bslot[slot][l] = (uint8_t)sl; sm.sloc[slot][l] = ssel; }
+                    if (leader) { sm.vloc[slot][l] = m; bs.bslot[slot][l] = (uint8_t)sl; }
                 }
             };
             {
@@ -1243,11 +1280,15 @@ k_rollout_greedy(StateView sv, int64_t env_offset, uint64_t seed, int piece_set,
             }
             __syncthreads();                               // phase B is complete: vloc / bslot / sloc of every slot
             // ---- phase S: the line-clearing legal placements of this warp's own 32 envs, one lane per item.  Their best
-            // keys go to best[slot of the env]: only this warp (this group's warps) touches those entries.
+            // keys go to best[slot of the env]: only this warp (this group's warps) touches those entries.  (Pooling the
+            // items over the CTA as K1 does -- in the greedy steady state this phase is 9 % of K3's instructions at 14 of
+            // 32 lanes -- costs two more barriers per step and measured -0.3 %: profiles/README.md, r2v.)
             const int grp = WPG == 1 ? warp : warp % NGROUPS, sub = WPG == 1 ? 0 : warp / NGROUPS;
             const int gslot = WPG == 1 ? myslot : (int)sm.slot_of[(grp << 5) + lane];
             const bool has = gslot != kNoSlot;
-            for_each_slow_item(has ? sm.sloc[gslot][0] : 0u, has ? sm.sloc[gslot][1] : 0u, gslot, lane, sub, WPG,
+            const uint32_t gpw = has ? sm.piece[sm.pid[gslot]] : 0u;
+            for_each_slow_item(has ? sm.sloc[gslot][0] & loc_mask<C>(gpw, 0) : 0u, has ? sm.sloc[gslot][1] & loc_mask<C>(gpw, 1) : 0u,
+                               gslot, lane, sub, WPG,
                                [&](int owner, int oslot, int l, int o, int cc) {
                 const uint32_t pw = sm.piece[sm.pid[oslot]];
                 const int n0 = pw & 3, w0 = (pw >> 2) & 7, n1 = (pw >> 5) & 3, obase = (pw >> 10) & 63;
