@@ -378,7 +378,8 @@ def run_ours(args):
         # launch of T placements, so the HBM fraction is tiny by construction; what bounds it is instruction issue (the
         # work is K1's enumeration + features fused with the policy and the env step): see issue_ruler.
         k3_bytes = 2 * E * (STATE_READ_BYTES + 8)
-        k3_issue = issue_ruler("k3", props.multi_processor_count, sm_hz)
+        # k3g: captured in the greedy steady state (the boards this timed region plays on); k3: boards after random play
+        k3_issue = issue_ruler("k3g", props.multi_processor_count, sm_hz) or issue_ruler("k3", props.multi_processor_count, sm_hz)
         out["roofline_step_kernel"] = {
             "kernel": "k_rollout_greedy<%d,%d> (K3): %d placements per env per launch, %d envs" % (C, R, T, E),
             "bound": "issue slots (integer / bit work); HBM sees the env state once per launch",
@@ -388,6 +389,7 @@ def run_ours(args):
                     "frac": k3_bytes / (ms / K * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": k3_bytes,
                     "traffic": (k3_issue or {}).get("dram_bytes_per_launch_ncu"), "peak_source": peak_src},
             "issue": k3_issue,
+            "issue_on_random_play_boards": issue_ruler("k3", props.multi_processor_count, sm_hz),
         }
 
         # ---- roofline of the afterstate kernel (K1, the north_star's roofline target), timed live

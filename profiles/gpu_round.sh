@@ -10,6 +10,6 @@ python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?
 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_ref_$tag.json 2>/dev/null
 python bench.py --steps 2 --warmup 3 --no-extras > $out/bench_plain_$tag.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $out/launches_bench_$tag.csv python bench.py --steps 2 --warmup 3 --no-extras > $out/ncu_lb_$tag.log 2>&1
-bash profiles/cap.sh $tag k1 k3 k2 k3r
+bash profiles/cap.sh $tag k1 k3 k3g k2 k3r
 ls -la $out | head -50
 echo done

@@ -64,6 +64,18 @@ TB_HD int ctz32(uint32_t x)  // x != 0
     return __builtin_ctz(x);
 #endif
 }
+// Hole depth of one column (state.py:216): for every vertical run of holes, the filled cells above it.  x = the column,
+// t = the top cell of every hole run.  The first run is handled without a branch, the others in a loop: most columns
+// have at most one, and the purely data-dependent loop ran with 6-9 of 32 lanes (10 % of K2's instructions).  Measured:
+// K1 -1.1 %, K2 -1.5 %; two branch-free runs cost K3 2 % (profiles/README.md, r2w).
+TB_HD int hole_depth_of(uint32_t x, uint32_t t)
+{
+    const int r1 = t ? ctz32(t) + 1 : 31;                        // no run at all: x >> 31 = 0 (columns are < 2^31)
+    int hd = popc32(x >> r1);
+    t &= t - 1u;
+    while (t) { hd += popc32(x >> (ctz32(t) + 1)); t &= t - 1u; }
+    return hd;
+}
 TB_HD uint32_t mask_lo(int k) { return (1u << k) - 1u; }          // k in [0, 31]
 TB_HD int height_of(uint32_t col) { return 32 - clz32(col); }      // 1 + highest filled row, 0 if empty
 TB_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -589,11 +601,7 @@ TB_HD void eval_full_tab(const uint32_t *col, const uint32_t *runtab, int *out6)
         hm |= hole;                                              // :215
         uint32_t t = hole & (x >> 1);                            // top cell of every vertical hole run
         ct += 1 + 2 * popc32(t);                                 // :194,:219-220,:242-243
-        while (t) {                                              // :216 filled cells above the run
-            const int r = ctz32(t);
-            hd += popc32(x >> (r + 1));
-            t &= t - 1;
-        }
+        hd += hole_depth_of(x, t);                               // :216 filled cells above the run
         wells = run_sum_acc<R, PERM>(runtab, L & Rt & ~x, wells);   // :222-233,:262-272 (heights <= R: no limit mask needed)
         if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh); // :203-204,:225-226,:246-248
         else rt += popc32(L & mask_lo(hL));                      // :254
@@ -682,7 +690,7 @@ TB_HD void build_env(const uint32_t *runtab, uint32_t *rec)
         uint32_t t = hole & (x >> 1);
         const int nr = popc32(t);
         ct += 1 + 2 * nr;
-        while (t) { const int r = ctz32(t); hd += popc32(x >> (r + 1)); t &= t - 1; }
+        hd += hole_depth_of(x, t);
         wells = run_sum_acc<R>(runtab, L & Rt & ~x, wells);
         if (h > 0) rt += imax(0, hL - h) + popc32((x ^ L) & mh);
         else rt += popc32(L & mask_lo(hL));
