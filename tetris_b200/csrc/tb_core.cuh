@@ -408,9 +408,27 @@ struct Eval {
 
 // hard-drop row of orientation `d` anchored at column c (tetromino.py: anchor_row = max(h - bottom)).
 // Static indexing over the board's columns so `col` can stay in registers.
+// Up to 12 columns the loops over the board's columns are branch-free: what the piece contributes to column k is cut out
+// of a 64-bit word that holds the piece's four per-column fields shifted to the anchor column (5-bit fields for the
+// bottom offsets, 4-bit fields for the cells).  The per-column `if (k - c < 4)` form ran each column's body with the 2-3
+// lanes of a warp whose piece covers that column (a quarter of the random rollout's instructions at 9-15 of 32 lanes).
 template <int C>
 TB_HD int anchor_from_cols(const uint32_t *col, uint32_t d, int c)
 {
+    if (C <= 12) {
+        uint32_t nb5 = 0u;                                       // per piece column: 31 - bot (a column without cells: 0)
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+            nb5 |= ((f >> 2) ? 31u - (f & 3u) : 0u) << (5 * dx);
+        }
+        const unsigned long long q = (unsigned long long)nb5 << (5 * c);   // fields beyond column C-1 are empty
+        int a = 0;
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            a = imax(a, height_of(col[k]) + (int)((uint32_t)(q >> (5 * k)) & 31u) - 31);   // h - bot, or below zero
+        return a;
+    }
     int a = 0;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
@@ -431,27 +449,48 @@ TB_HD int place_and_clear(uint32_t *col, uint32_t d, int c, int &a_out, uint32_t
     using S = Shape<C, R>;
     const int a = anchor_from_cols<C>(col, d, c);
     uint32_t full = S::ALL;
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-        const unsigned dx = (unsigned)(k - c);
-        if (dx < 4u) {
-            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
-            col[k] |= mask_lo((int)(f >> 2)) << (a + (int)(f & 3u));
-        }
-        full &= col[k];
-    }
-    full &= mask_lo(desc_chg(d)) << a;                           // only changed_lines are tested (state.py:122)
     int cells = 0;
-    if (full) {
+    if (C <= 12) {
+        uint32_t p4 = 0u;                                        // per piece column: its cells relative to the anchor row
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+            p4 |= (mask_lo((int)(f >> 2)) << (f & 3u)) << (4 * dx);
+        }
+        const unsigned long long q = (unsigned long long)p4 << (4 * c);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            col[k] |= ((uint32_t)(q >> (4 * k)) & 15u) << a;
+            full &= col[k];
+        }
+        full &= mask_lo(desc_chg(d)) << a;                       // only changed_lines are tested (state.py:122)
+        if (full) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) cells += popc32((((uint32_t)(q >> (4 * k)) & 15u) << a) & full);
+            clear_rows<C>(col, full);
+        }
+    } else {
 #pragma unroll
         for (int k = 0; k < C; ++k) {
             const unsigned dx = (unsigned)(k - c);
             if (dx < 4u) {
                 const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
-                cells += popc32((mask_lo((int)(f >> 2)) << (a + (int)(f & 3u))) & full);
+                col[k] |= mask_lo((int)(f >> 2)) << (a + (int)(f & 3u));
             }
+            full &= col[k];
         }
-        clear_rows<C>(col, full);
+        full &= mask_lo(desc_chg(d)) << a;                       // only changed_lines are tested (state.py:122)
+        if (full) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const unsigned dx = (unsigned)(k - c);
+                if (dx < 4u) {
+                    const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+                    cells += popc32((mask_lo((int)(f >> 2)) << (a + (int)(f & 3u))) & full);
+                }
+            }
+            clear_rows<C>(col, full);
+        }
     }
     uint32_t any = 0;
 #pragma unroll
@@ -1019,6 +1058,51 @@ TB_HD uint32_t spread16(uint32_t x)
     return x;
 }
 
+// bit i of the low half -> bit 2i, bit i of the high half -> bit 2i + 1 (outer perfect shuffle): the loop-local slot bits
+// c * 2 + o of a column loop with two orientations, from the orientations' column masks packed as two 16-bit halves
+TB_HD uint32_t interleave16(uint32_t x)
+{
+    uint32_t t;
+    t = (x ^ (x >> 8)) & 0x0000FF00u; x ^= t ^ (t << 8);
+    t = (x ^ (x >> 4)) & 0x00F000F0u; x ^= t ^ (t << 4);
+    t = (x ^ (x >> 2)) & 0x0C0C0C0Cu; x ^= t ^ (t << 2);
+    t = (x ^ (x >> 1)) & 0x22222222u; x ^= t ^ (t << 1);
+    return x;
+}
+
+// Per orientation, for the column-parallel legality test of valid_slots: a piece column dx pokes above row R when its
+// board column is taller than R - 4 + k, k = 4 - ph + bot[dx] in 0..3.  With the four height classes G_0..G_3 packed as the
+// 16-bit fields of a 64-bit word, field k is picked by ONE byte permute; this table holds its selector for every dx
+// (16 bits each: bytes 2k, 2k+1 into both halves of the result).
+struct PokeImage { unsigned long long v[kNumOris]; };
+constexpr PokeImage make_poke_image()
+{
+    PokeImage t{};
+    for (int i = 0; i < kNumOris; ++i) {
+        const uint32_t d = kOriHost[i];
+        const int ph = (int)((d >> 28) & 7u);
+        unsigned long long v = 0;
+        for (int dx = 0; dx < 4; ++dx) {
+            const int k = (4 - ph + (int)((d >> (3 + 5 * dx)) & 3u)) & 3;   // columns beyond the piece's width: unused
+            v |= (unsigned long long)(2u * (uint32_t)k * 0x1111u + 0x1010u) << (16 * dx);
+        }
+        t.v[i] = v;
+    }
+    return t;
+}
+static constexpr PokeImage kPokeHost = make_poke_image();
+#if defined(__CUDACC__)
+static __constant__ PokeImage c_poke = make_poke_image();
+#endif
+TB_HD unsigned long long poke_sel(int oi)
+{
+#if defined(__CUDA_ARCH__)
+    return c_poke.v[oi];
+#else
+    return kPokeHost.v[oi];
+#endif
+}
+
 template <int C, int R, bool ANY_ONLY = false>
 TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uint32_t *ori)
 {
@@ -1050,7 +1134,7 @@ TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uin
 #pragma unroll
         for (int j = 0; j < 4; ++j) row[j] = ((acc0 >> (8 * j)) & 0xFFu) | (((acc1 >> (8 * j)) & 0xFFu) << 8);
         const uint32_t g3 = row[3], g2 = g3 | row[2], g1 = g2 | row[1], g0 = g1 | row[0];
-        const uint64_t gg = (uint64_t)g0 | (uint64_t)g1 << 16 | (uint64_t)g2 << 32 | (uint64_t)g3 << 48;
+        const uint32_t gg_lo = g0 | g1 << 16, gg_hi = g2 | g3 << 16;  // G_0..G_3 as 16-bit fields (poke_sel picks one)
         // near-full rows among R-3 .. R-1: span of their empty cells, lo | hi << 8 | 1 << 16 (0 = not near-full)
         uint32_t span[3] = {0u, 0u, 0u};
         const bool near = popc32(row[1]) >= C - 4 || popc32(row[2]) >= C - 4 || popc32(row[3]) >= C - 4;
@@ -1075,20 +1159,25 @@ TB_HD unsigned long long valid_slots(const uint32_t *col, uint32_t pw, const uin
                     if (span[j] != 0u && hi - lo < w) rescue |= mask_lo(lo + 1) & ~mask_lo(imax(hi - w + 1, 0));
                 }
             }
+            uint32_t okp = 0u, cdp = 0u;                       // per orientation: 16 bits of legal / to-be-tested columns
 #pragma unroll 1
             for (int o = 0; o < n; ++o) {
-                const uint32_t d = ori[ob + o];
-                const int ph = desc_ph(d);
+                const unsigned long long ps = poke_sel(ob + o);
                 uint32_t bad = 0u;
 #pragma unroll
                 for (int dx = 0; dx < 4; ++dx)
-                    if (dx < w) bad |= ((uint32_t)(gg >> (16 * (4 - ph + desc_bot(d, dx)))) & 0xFFFFu) >> dx;
+                    if (dx < w) {
+                        uint32_t g = prmt(gg_lo, gg_hi, (uint32_t)(ps >> (16 * dx)));   // field k(dx), in both halves
+                        if (C > 12) g &= 0xFFFFu;              // narrower boards: `range` cuts what the shift lets in
+                        bad |= g >> dx;
+                    }
                 const uint32_t ok = ~bad & range, cd = bad & rescue & range;
                 if (ANY_ONLY && ok != 0u) return 1ull;
-                // loop-local slot of (column c, orientation o) = c * n + o
-                m |= (unsigned long long)(n == 2 ? spread16(ok) << o : ok) << sbase;
-                cs |= (unsigned long long)(n == 2 ? spread16(cd) << o : cd) << sbase;
+                okp |= ok << (16 * o); cdp |= cd << (16 * o);
             }
+            // loop-local slot of (column c, orientation o) = c * n + o
+            m |= (unsigned long long)(n == 2 ? interleave16(okp) : okp) << sbase;
+            if (cdp != 0u) cs |= (unsigned long long)(n == 2 ? interleave16(cdp) : cdp) << sbase;
         }
         if (ANY_ONLY && m != 0ull) return 1ull;
         while (cs != 0ull) {                                   // rare: the one copy of the exact test
