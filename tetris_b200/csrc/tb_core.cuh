@@ -441,6 +441,18 @@ TB_HD int anchor_from_cols(const uint32_t *col, uint32_t d, int c)
     return a;
 }
 
+// The cells of orientation `d`, per piece column relative to the anchor row, as four 4-bit fields
+TB_HD uint32_t piece_cells4(uint32_t d)
+{
+    uint32_t p4 = 0u;
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+        const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+        p4 |= (mask_lo((int)(f >> 2)) << (f & 3u)) << (4 * dx);
+    }
+    return p4;
+}
+
 // Place orientation `d` at column c on `col` (in place), clear lines, report a/full/terminal.
 // Returns the number of piece cells in the cleared rows (for the eroded feature).
 template <int C, int R>
@@ -451,13 +463,7 @@ TB_HD int place_and_clear(uint32_t *col, uint32_t d, int c, int &a_out, uint32_t
     uint32_t full = S::ALL;
     int cells = 0;
     if (C <= 12) {
-        uint32_t p4 = 0u;                                        // per piece column: its cells relative to the anchor row
-#pragma unroll
-        for (int dx = 0; dx < 4; ++dx) {
-            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
-            p4 |= (mask_lo((int)(f >> 2)) << (f & 3u)) << (4 * dx);
-        }
-        const unsigned long long q = (unsigned long long)p4 << (4 * c);
+        const unsigned long long q = (unsigned long long)piece_cells4(d) << (4 * c);
 #pragma unroll
         for (int k = 0; k < C; ++k) {
             col[k] |= ((uint32_t)(q >> (4 * k)) & 15u) << a;
@@ -1028,15 +1034,21 @@ TB_HD bool placement_valid(const uint32_t *col, uint32_t d, int c, int hmax)
     const int top = imax(hmax, a + desc_ph(d));
     if (top <= R) return true;
     uint32_t full = S::ALL;
+    if (C <= 12) {                                               // branch-free over the columns, as in place_and_clear
+        const unsigned long long q = (unsigned long long)piece_cells4(d) << (4 * c);
 #pragma unroll
-    for (int k = 0; k < C; ++k) {
-        const unsigned dx = (unsigned)(k - c);
-        uint32_t x = col[k];
-        if (dx < 4u) {
-            const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
-            x |= mask_lo((int)(f >> 2)) << (a + (int)(f & 3u));
+        for (int k = 0; k < C; ++k) full &= col[k] | (((uint32_t)(q >> (4 * k)) & 15u) << a);
+    } else {
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const unsigned dx = (unsigned)(k - c);
+            uint32_t x = col[k];
+            if (dx < 4u) {
+                const uint32_t f = (d >> (3 + 5 * dx)) & 31u;
+                x |= mask_lo((int)(f >> 2)) << (a + (int)(f & 3u));
+            }
+            full &= x;
         }
-        full &= x;
     }
     full &= mask_lo(desc_chg(d)) << a;
     return top - popc32(full) <= R;
