@@ -148,3 +148,43 @@ extern "C" int hc_table_images()
     if (!run_image_ok<9>()) return -9;
     return 0;
 }
+
+// The bit helpers of the column-parallel legality test and of the branch-free placement, against plain restatements.
+extern "C" int hc_bit_helpers()
+{
+    // interleave16: bit i of the low half -> bit 2i, of the high half -> bit 2i + 1
+    uint32_t x = 0x9E3779B9u;
+    for (int it = 0; it < 4096; ++it) {
+        x = x * 1664525u + 1013904223u;
+        uint32_t want = 0u;
+        for (int i = 0; i < 16; ++i) want |= ((x >> i) & 1u) << (2 * i) | ((x >> (16 + i)) & 1u) << (2 * i + 1);
+        if (interleave16(x) != want) return -1;
+        if ((spread16(x & 0xFFFFu) | spread16(x >> 16) << 1) != want) return -2;
+    }
+    for (int i = 0; i < kNumOris; ++i) {
+        const uint32_t d = kOriHost[i];
+        // poke_sel: the selector of piece column dx picks the 16-bit field k = 4 - ph + bot[dx] of a 64-bit word
+        const uint32_t lo = 0x22221111u, hi = 0x44443333u;            // field k holds 0x1111 * (k + 1)
+        for (int dx = 0; dx < desc_w(d); ++dx) {
+            const int k = 4 - desc_ph(d) + desc_bot(d, dx);
+            if (k < 0 || k > 3) return -(100 + i);
+            if ((prmt(lo, hi, (uint32_t)(poke_sel(i) >> (16 * dx))) & 0xFFFFu) != 0x1111u * (uint32_t)(k + 1)) return -(200 + i);
+        }
+        // piece_cells4: field dx = the column's cells relative to the anchor row
+        for (int dx = 0; dx < 4; ++dx) {
+            const uint32_t want = desc_len(d, dx) ? mask_lo(desc_len(d, dx)) << desc_bot(d, dx) : 0u;
+            if (((piece_cells4(d) >> (4 * dx)) & 15u) != want) return -(300 + i);
+        }
+    }
+    // hole_depth_of against the plain loop
+    for (int it = 0; it < 4096; ++it) {
+        x = x * 1664525u + 1013904223u;
+        const uint32_t col = x & 0x00FFFFFFu;
+        const int h = height_of(col);
+        const uint32_t hole = ~col & mask_lo(h), t = hole & (col >> 1);
+        int want = 0;
+        for (uint32_t tt = t; tt; tt &= tt - 1u) want += popc32(col >> (ctz32(tt) + 1));
+        if (hole_depth_of(col, t) != want) return -3;
+    }
+    return 0;
+}

@@ -196,3 +196,10 @@ def test_compile_time_table_images(hc):
     by the tile kernels) equal run_tab_entry / decode_ori word for word, for every compiled board height."""
     hc.hc_table_images.restype = C.c_int
     assert hc.hc_table_images() == 0
+
+
+def test_bit_helpers(hc):
+    """interleave16, the byte-permute selectors of the legality test (poke_sel), piece_cells4 and hole_depth_of against
+    plain restatements (the kernels' results are compared with the oracle elsewhere; this pins the helpers themselves)."""
+    hc.hc_bit_helpers.restype = C.c_int
+    assert hc.hc_bit_helpers() == 0
