@@ -567,6 +567,40 @@ def gen_rollouts(ref):
     np.savez_compressed(os.path.join(HERE, "rollouts.npz"), **out)
 
 
+def gen_learner(ref):
+    """The learner math of the reference (utils.py:26-45) on seeded inputs: compute_action_probabilities,
+    grad_of_log_action_probabilities and softmax, per env over its legal afterstates (slot order), for three temperatures.
+    Features are float32 half-integers in the range the board features take; legal-slot masks are arbitrary subsets."""
+    u = ref["utils"]
+    rng = np.random.RandomState(20260)
+    n, a_max = 96, 34
+    feats = (rng.randint(-40, 400, size=(n, a_max, 8)) * 0.5).astype(np.float32)
+    feats[:, :, 6] = rng.randint(0, 17, size=(n, a_max))                      # eroded cells: small integers
+    valid = np.zeros(n, np.uint64)
+    for e in range(n):
+        k = 1 + rng.randint(a_max) if e else a_max                             # env 0: every slot legal
+        for sl in rng.choice(a_max, size=k, replace=False):
+            valid[e] |= np.uint64(1) << np.uint64(sl)
+    weights = np.array([-2.4, -1.9, -1.3, -1.2, -1.0, -0.9, 0.6, -0.1])
+    temps = np.array([1.0, 0.25, 7.5])
+    bits = ((valid[:, None] >> np.arange(a_max, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    actions = np.array([rng.choice(np.nonzero(b)[0]) for b in bits], np.int32)      # enumeration slot of the chosen action
+    probs = np.zeros((len(temps), n, a_max))
+    grads = np.zeros((len(temps), n, 8))
+    soft = np.zeros((n, a_max))
+    for e in range(n):
+        fe = feats[e][bits[e]].astype(np.float64)
+        k = int(np.nonzero(np.nonzero(bits[e])[0] == actions[e])[0][0])
+        for ti, t in enumerate(temps):
+            pr = u.compute_action_probabilities(fe, weights, t)
+            probs[ti, e][bits[e]] = pr
+            grads[ti, e] = u.grad_of_log_action_probabilities(fe, pr, k)
+        soft[e][bits[e]] = u.softmax(fe.dot(weights))
+    np.savez_compressed(os.path.join(HERE, "learner.npz"), feats=feats, valid=valid, weights=weights, temps=temps,
+                        actions=actions, probs=probs, grads=grads, softmax=soft)
+    print("learner.npz: %d envs x %d temperatures" % (n, len(temps)))
+
+
 def main():
     ref = load_reference()
     only = sys.argv[1:]
@@ -579,6 +613,7 @@ def main():
     gen_afterstates_dense(ref)
     gen_rollouts(ref)
     gen_fitness(ref)
+    gen_learner(ref)
     gen_trace(ref, "7p_10x20_random", 10, 20, 1, 32, 160, "random", None, 0x5EED)
     gen_trace(ref, "2p_10x10_random_dir", 10, 10, 0, 16, 120, "random", DIRECTIONS, 11)
     gen_trace(ref, "7p_6x12_random", 6, 12, 1, 16, 120, "random", None, 12)

@@ -90,6 +90,25 @@ def test_utils_math():
     assert utils.print_board_to_string(S) == "\n|  ██|\n|    |\n|██  |\n"       # top row first (utils.py:179-191)
 
 
+def test_learner_math_vs_reference_fixture():
+    """utils.compute_action_probabilities / grad_of_log_action_probabilities / softmax (utils.py:26-45) of the host mirror
+    against vectors recorded from the reference's own functions (tests/golden/learner.npz, make_golden.py gen_learner).
+    Same NumPy expressions in the same order: bit-identical."""
+    from golden_util import load
+    from tetris import utils
+    g = load("learner")
+    a_max = g["feats"].shape[1]
+    bits = ((g["valid"][:, None] >> np.arange(a_max, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    for e in range(len(bits)):
+        fe = g["feats"][e][bits[e]].astype(np.float64)
+        k = int(np.nonzero(np.nonzero(bits[e])[0] == g["actions"][e])[0][0])
+        for ti, t in enumerate(g["temps"]):
+            p = utils.compute_action_probabilities(fe, g["weights"], t)
+            assert np.array_equal(p, g["probs"][ti, e][bits[e]]), (e, t)
+            assert np.array_equal(utils.grad_of_log_action_probabilities(fe, p, k), g["grads"][ti, e]), (e, t)
+        assert np.array_equal(utils.softmax(fe.dot(g["weights"])), g["softmax"][e][bits[e]])
+
+
 def test_state_host_helpers():
     from tetris import state
     rep = np.zeros((14, 10), int)

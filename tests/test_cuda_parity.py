@@ -369,6 +369,30 @@ def test_action_probabilities_vs_numpy():
         assert np.allclose(probs.sum(axis=1), 1.0, atol=1e-12)
 
 
+def test_action_probabilities_vs_reference_fixture():
+    """tb_action_probabilities against vectors recorded from the reference's own utils.compute_action_probabilities /
+    grad_of_log_action_probabilities (utils.py:26-38; tests/golden/learner.npz): arbitrary legal-slot subsets, three
+    temperatures.  float64 on the device; tolerance 1e-12 absolute on probabilities, 1e-10 on the gradient (the device's
+    exp differs from NumPy's in the last ulp; sums run in slot order on both sides)."""
+    torch = _torch()
+    from golden_util import load
+    from tetris_b200 import BatchedTetris
+    g = load("learner")
+    n, a_max = g["feats"].shape[:2]
+    env = BatchedTetris(10, 20, n, piece_set=1, seed=1)
+    assert env.a_max == a_max
+    feats = torch.as_tensor(g["feats"]).cuda()
+    valid = torch.as_tensor(g["valid"].view(np.int64)).cuda()
+    bits = ((g["valid"][:, None] >> np.arange(a_max, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    for ti, t in enumerate(g["temps"]):
+        probs, grad = env.action_probabilities(feats, valid, g["weights"], temperature=float(t),
+                                               actions=torch.as_tensor(g["actions"]))
+        probs, grad = probs.cpu().numpy(), grad.cpu().numpy()
+        assert not probs[~bits].any()
+        assert np.allclose(probs, g["probs"][ti], rtol=0, atol=1e-12), t
+        assert np.allclose(grad, g["grads"][ti], rtol=0, atol=1e-10), t
+
+
 @pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 700])
 def test_ragged_sizes(n):
     """Env counts around the warp / CTA-tile boundaries (tile = 256 envs): K1, K2, K3 against the oracle, with feature
