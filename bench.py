@@ -11,6 +11,7 @@ env (= example_play.py:11-21 loop bodies) followed, for N > 1, by the NCCL all-r
 Weak scaling: envs per GPU fixed, env ids global (rank r owns [r*E, (r+1)*E)), no per-step communication.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -66,20 +67,22 @@ def config_of(args, n_gpus):
 
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (every 20 ms).  nvidia-smi block-buffers its
+    output into the pipe, so lines arrive in bursts: the samples of the timed region are selected by nvidia-smi's own
+    timestamp against the wall clock at mark_begin / mark_end, not by when they arrived."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
-        self.lo = self.hi = None
+        self.index, self.lines, self.proc, self.thread = index, [], None, None
+        self.t0 = self.t1 = None
 
     def mark_begin(self):
-        self.lo = len(self.lines)
+        self.t0 = datetime.datetime.now()
 
     def mark_end(self):
-        self.hi = len(self.lines)
+        self.t1 = datetime.datetime.now()
 
     def start(self):
         try:
@@ -95,32 +98,41 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    @staticmethod
+    def parse(line):
+        """(time, sm MHz, max sm MHz, power W, [reason flags]) of one csv line, or None."""
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 10:
+            return None
+        try:
+            ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+            return ts, float(f[2]), float(f[3]), float(f[4]), [x.lower().startswith("active") for x in f[6:10]]
+        except ValueError:
+            return None
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)                                     # let the sample of the last 20 ms be written
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
+        if self.thread is not None:
+            self.thread.join(timeout=5)                      # drain what was still buffered in the pipe
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        lines = self.lines[self.lo:self.hi] if self.lo is not None and self.hi is not None and self.hi > self.lo \
-            else self.lines[(self.lo or 0):]
-        for ln in lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for k, name in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        rows = [r for r in (self.parse(ln) for ln in list(self.lines)) if r is not None]
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        where = "timed region"
+        if not inside and self.t0 is not None:               # a region shorter than the sampling period: nearest samples
+            inside = sorted(rows, key=lambda r: abs((r[0] - self.t0).total_seconds()))[:3]
+            where = "nearest to the timed region"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({names[k] for r in inside for k in range(4) if r[4][k]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "power_w_max": max((r[3] for r in inside), default=None), "samples": len(sm), "sampled": where,
+                "reasons": reasons}
 
 
 def measured_peak_gbs():
