@@ -4,6 +4,7 @@ There is no CPU fallback: if the CUDA extension cannot be loaded every entry poi
 """
 import ctypes as C
 import os
+import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -44,13 +45,21 @@ def _stale():
     return _newer(SOURCES, SO_PATH)
 
 
+def _code_only(text):
+    """C / CUDA source without comments and with white space collapsed: what the compiler sees, for source_hash."""
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    return re.sub(r"\s+", " ", text).strip()
+
+
 def source_hash():
-    """sha256 (first 16 hex digits) over the kernel sources: profiles/<kernel>_latest.json records the value its ncu capture
-    was taken from, and bench.py flags quoted capture figures as stale when the sources have changed since."""
+    """sha256 (first 16 hex digits) over the CODE of the kernel sources (comments and white space do not count):
+    profiles/<kernel>_latest.json records the value its ncu capture was taken from, and bench.py flags quoted capture
+    figures as stale when the code has changed since."""
     import hashlib
     h = hashlib.sha256()
     for f in ("tb_core.cuh", "tb_kernels.cuh", "tb_shape.h"):
-        h.update(open(os.path.join(CSRC, f), "rb").read())
+        h.update(_code_only(open(os.path.join(CSRC, f)).read()).encode())
     return h.hexdigest()[:16]
 
 

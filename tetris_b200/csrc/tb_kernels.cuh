@@ -293,8 +293,8 @@ __device__ __forceinline__ void stage_run_table(uint32_t *s_run)
     }
 }
 
-// s_run: the run-sum table, in STATIC shared memory (its address is then an immediate of every lookup; inside the
-// dynamic block each of the ~9 lookups per afterstate paid an add of the block's base)
+// s_run: the run-sum table, placed by run_tab_place inside a static shared-memory array (run_sum_acc then forms an entry's
+// address with one LOP3).  odesc / job: K3 reads them from shared memory, K1 from constant memory (c_odesc / c_job).
 template <int C, int R, int TILE>
 __device__ __forceinline__ void stage_cta(CtaSmem<C, R, TILE> &sm, uint32_t *s_run)
 {
